@@ -1,0 +1,274 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//
+//   * operands: TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> smem ring, K-major for both A and W
+//     (W is a torch `nn.Linear.weight` [out,in], i.e. already K-major: no transposes anywhere)
+//   * math: tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), 128 x BN x 16 per instruction, accumulators in TMEM,
+//     double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//   * roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 = epilogue
+//   * epilogue: tcgen05.ld -> per-warp smem transpose -> coalesced global access with
+//     bias / activation / fp32 residual / row remap fused; writes fp32 and/or bf16 (optionally bf16 hi+lo split)
+//
+// Replaces the cuBLAS/MKL calls behind nn.Linear / nn.MultiheadAttention in_proj,out_proj / 1x1 Conv2d of the
+// reference (segmentation/denseclip/models.py:275-281,287-289; denseclip.py:198,616).
+#pragma once
+#include "ptx.cuh"
+
+namespace dclip {
+
+enum GemmAct : int {
+  ACT_NONE = 0,
+  ACT_QUICKGELU = 1,          // x * sigmoid(1.702 x)  (models.py:252-254), tanh.approx form (bf16-accurate)
+  ACT_QUICKGELU_PRECISE = 2,  // same, exp/rcp form (fp32-accurate; used by the split-bf16 "fp32" path)
+  ACT_GELU_ERF = 3,           // nn.GELU() exact (models.py:363)
+  ACT_RELU = 4,
+};
+
+struct GemmParams {
+  int M, N, K;            // logical problem (K per segment when split_in)
+  int split_in;           // 1: A=[Ah|Al] (2K cols), W=[Wh|Wl] (2K cols); computes Ah*Wh + Al*Wh + Ah*Wl
+  const float* bias;      // [N] or null
+  int act;                // GemmAct
+  const float* residual;  // fp32 or null; row = res_mod ? 1 + m % remap_P : out_row
+  int ldr;
+  int res_mod;
+  int remap_P, remap_Nt;  // remap_P > 0: out_row = (m / P) * Nt + 1 + m % P   (patch-embed -> token rows)
+  float* out_f32;         // [*, ldc] or null
+  int ldc;
+  __nv_bfloat16* out_bf16;  // [*, ldcb] or null
+  int ldcb;
+  int split_out;          // 1: also write lo = bf16(v - hi) at column offset split_out_off
+  int split_out_off;
+  float out_scale;        // applied after activation, before residual (1.0f default)
+};
+
+// Compile-time epilogue specialisation. ACT < 0 / FLAGS < 0 select the generic (runtime-checked) epilogue.
+enum GemmEpiFlags : int { EPI_RESID = 1, EPI_OUT_F32 = 2, EPI_OUT_BF16 = 4, EPI_SPLIT = 8, EPI_REMAP = 16 };
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 196608 / STAGE_BYTES;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int STG_WARP_BYTES = 32 * 32 * 4;  // one 32x32 fp32 chunk per epilogue warp, XOR-swizzled (no padding)
+  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int THREADS = 128 + EPI_WARPS * 32;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case ACT_QUICKGELU: return x * (0.5f + 0.5f * tanh_approx(0.851f * x));
+    case ACT_QUICKGELU_PRECISE: return x / (1.0f + __expf(-1.702f * x));
+    case ACT_GELU_ERF: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    case ACT_RELU: return fmaxf(x, 0.0f);
+    default: return x;
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ float apply_act_t(float x, int act_rt) {
+  if constexpr (ACT < 0) return apply_act(x, act_rt);
+  else if constexpr (ACT == ACT_QUICKGELU) return x * (0.5f + 0.5f * tanh_approx(0.851f * x));
+  else if constexpr (ACT == ACT_NONE) return x;
+  else return apply_act(x, ACT);
+}
+
+template <int BN, int ACT, int FLAGS>
+__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int kseg = (p.K + BK - 1) / BK;
+  const int num_k = p.split_in ? 3 * kseg : kseg;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("dclip gemm: dynamic smem base not 1024B aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], Cfg::EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          int a_col = kb * BK, b_col = kb * BK;
+          if (p.split_in) {
+            const int seg = kb / kseg, off = (kb - seg * kseg) * BK;
+            a_col = (seg == 1 ? p.K : 0) + off;
+            b_col = (seg == 2 ? p.K : 0) + off;
+          }
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(sa, &tmA, &full_bar[stage], a_col, m_blk * BM);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], b_col, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_ss_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_k - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------- epilogue -----------------------------------
+    // 8 warps: warp pair (w, w+4) shares TMEM lane quarter q = w & 3 and splits the tile's 32-column chunks.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint8_t* stg = smem + STAGES * Cfg::STAGE_BYTES + (warp - 4) * Cfg::STG_WARP_BYTES;
+    const bool has_res = FLAGS >= 0 ? bool(FLAGS & EPI_RESID) : p.residual != nullptr;
+    const bool has_f32 = FLAGS >= 0 ? bool(FLAGS & EPI_OUT_F32) : p.out_f32 != nullptr;
+    const bool has_b16 = FLAGS >= 0 ? bool(FLAGS & EPI_OUT_BF16) : p.out_bf16 != nullptr;
+    const bool has_split = FLAGS >= 0 ? bool(FLAGS & EPI_SPLIT) : p.split_out != 0;
+    const bool has_remap = FLAGS >= 0 ? bool(FLAGS & EPI_REMAP) : p.remap_P > 0;
+    const int sub = lane >> 3;      // row within a group of 4 rows handled per warp instruction
+    const int cq = lane & 7;        // 4-column group within the 32-column chunk
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const int row0 = m_blk * BM + q * 32;
+      const int rows_valid = min(32, p.M - row0);  // may be <= 0
+      // per-lane output / residual row offsets for its 8 rows (row = row0 + 4*k + sub)
+      size_t orow[8], rrow[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int m = row0 + 4 * k + sub;
+        orow[k] = m;
+        rrow[k] = m;
+        if (has_remap) {
+          const int bi = m / p.remap_P, pm = m - bi * p.remap_P;
+          orow[k] = size_t(bi) * p.remap_Nt + 1 + pm;
+          rrow[k] = p.res_mod ? size_t(1 + pm) : orow[k];
+        }
+      }
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = half; chunk < BN / 32; chunk += 2) {
+        const int c = n_blk * BN + chunk * 32 + 4 * cq;
+        const bool col_ok = c < p.N;  // N % 4 == 0 is required by the launcher
+        // residual prefetch (issued before the TMEM load so its latency overlaps)
+        float4 rr[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res && col_ok && 4 * k + sub < rows_valid)
+            rr[k] = *reinterpret_cast<const float4*>(p.residual + rrow[k] * p.ldr + c);
+        }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok) b4 = *reinterpret_cast<const float4*>(p.bias + c);
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + as * BN + chunk * 32 + (uint32_t(q * 32) << 16), r);
+        tmem_wait_ld();
+        // row-per-lane -> staging (16B chunk j of row `lane` lands at physical chunk j ^ (lane & 7))
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        if (col_ok) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int i = 4 * k + sub;
+            if (i < rows_valid) {
+              float4 v = *reinterpret_cast<const float4*>(stg + i * 128 + ((cq ^ (i & 7)) << 4));
+              v.x = apply_act_t<ACT>(v.x + b4.x, p.act) * p.out_scale + rr[k].x;
+              v.y = apply_act_t<ACT>(v.y + b4.y, p.act) * p.out_scale + rr[k].y;
+              v.z = apply_act_t<ACT>(v.z + b4.z, p.act) * p.out_scale + rr[k].z;
+              v.w = apply_act_t<ACT>(v.w + b4.w, p.act) * p.out_scale + rr[k].w;
+              if (has_f32) *reinterpret_cast<float4*>(p.out_f32 + orow[k] * p.ldc + c) = v;
+              if (has_b16) {
+                const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
+                *reinterpret_cast<uint2*>(p.out_bf16 + orow[k] * p.ldcb + c) = make_uint2(h0, h1);
+                if (has_split) {
+                  const uint32_t l0 = pack_bf16x2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xffff0000u));
+                  const uint32_t l1 = pack_bf16x2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xffff0000u));
+                  *reinterpret_cast<uint2*>(p.out_bf16 + orow[k] * p.ldcb + p.split_out_off + c) = make_uint2(l0, l1);
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace dclip

@@ -1,0 +1,181 @@
+// Host-side helpers: error plumbing, driver entry point for cuTensorMapEncodeTiled (no link-time libcuda
+// dependency, so the library loads on a machine without a driver), tensor-map builders, GEMM launcher.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "gemm_tcgen05.cuh"
+
+namespace dclip {
+
+struct Error {
+  std::string msg;
+};
+
+#define DCLIP_CHECK_CUDA(expr)                                                                       \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      char _buf[512];                                                                                \
+      snprintf(_buf, sizeof(_buf), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+               __LINE__);                                                                            \
+      throw ::dclip::Error{_buf};                                                                    \
+    }                                                                                                \
+  } while (0)
+
+#define DCLIP_REQUIRE(cond, ...)                                                  \
+  do {                                                                            \
+    if (!(cond)) {                                                                \
+      char _buf[512];                                                             \
+      int _n = snprintf(_buf, sizeof(_buf), "requirement failed: %s: ", #cond);   \
+      snprintf(_buf + _n, sizeof(_buf) - _n, __VA_ARGS__);                        \
+      throw ::dclip::Error{_buf};                                                 \
+    }                                                                             \
+  } while (0)
+
+inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  if (!fn) throw Error{"cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)"};
+  return fn;
+}
+
+// bf16 tensor map, up to 4 dims (innermost first). strides_bytes has rank-1 entries (dims 1..rank-1).
+inline CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                  const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  DCLIP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base %p not 16B aligned", base);
+  for (int i = 0; i + 1 < rank; ++i)
+    DCLIP_REQUIRE(strides_bytes[i] % 16 == 0, "tensor map stride[%d]=%llu not a multiple of 16B", i,
+                  (unsigned long long)strides_bytes[i]);
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  cuuint64_t gdim[5] = {1, 1, 1, 1, 1};
+  cuuint64_t gstr[4] = {0, 0, 0, 0};
+  cuuint32_t bdim[5] = {1, 1, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = get_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", int(r),
+             rank, (unsigned long long)gdim[0], (unsigned long long)gdim[1], bdim[0], bdim[1]);
+    throw Error{buf};
+  }
+  return tm;
+}
+
+// row-major [rows, cols] bf16 matrix with leading dimension ld (elements); box = {64 cols, box_rows}
+inline CUtensorMap make_tmap_2d_bf16(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  uint64_t dims[2] = {cols, rows};
+  uint64_t str[1] = {ld * 2};
+  uint32_t box[2] = {64, box_rows};
+  return make_tmap_bf16(base, 2, dims, str, box);
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+struct GemmOperands {
+  const __nv_bfloat16* A;
+  int lda;  // elements
+  const __nv_bfloat16* W;
+  int ldw;
+};
+
+// A GEMM launch with its tensor maps pre-encoded (cuTensorMapEncodeTiled is a driver call; plans are built once per
+// (buffer, shape) and replayed, which also makes the forward CUDA-graph capturable without host work).
+struct GemmPlan {
+  CUtensorMap tmA, tmB;
+  GemmParams p;
+  int bn = 0;
+  int grid = 0;
+};
+
+template <int BN, int ACT, int FLAGS>
+inline void launch_gemm_inst(const GemmPlan& plan, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, FLAGS>;
+  if (!attr_set) {
+    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<plan.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmA, plan.tmB, plan.p);
+  DCLIP_CHECK_CUDA(cudaGetLastError());
+}
+
+template <int BN>
+inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
+  const GemmParams& p = plan.p;
+  const int flags = (p.residual ? EPI_RESID : 0) | (p.out_f32 ? EPI_OUT_F32 : 0) | (p.out_bf16 ? EPI_OUT_BF16 : 0) |
+                    (p.split_out ? EPI_SPLIT : 0) | (p.remap_P > 0 ? EPI_REMAP : 0);
+  // hot ViT-block epilogues get compile-time specialisations; everything else takes the generic instantiation
+  if (p.act == ACT_NONE && flags == EPI_OUT_BF16) return launch_gemm_inst<BN, ACT_NONE, EPI_OUT_BF16>(plan, stream);
+  if (p.act == ACT_QUICKGELU && flags == EPI_OUT_BF16) return launch_gemm_inst<BN, ACT_QUICKGELU, EPI_OUT_BF16>(plan, stream);
+  if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32))
+    return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32>(plan, stream);
+  return launch_gemm_inst<BN, -1, -1>(plan, stream);
+}
+
+// bn = 0: choose automatically.
+inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int bn = 0, int max_ctas = 0) {
+  DCLIP_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "bad GEMM shape %d %d %d", p.M, p.N, p.K);
+  DCLIP_REQUIRE(p.N % 4 == 0, "GEMM N=%d must be a multiple of 4 (vectorised epilogue)", p.N);
+  DCLIP_REQUIRE(p.K % 8 == 0 && op.lda % 8 == 0 && op.ldw % 8 == 0, "GEMM K/lda/ldw must be multiples of 8 (K=%d)", p.K);
+  if (p.out_f32) DCLIP_REQUIRE(p.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0, "out_f32 alignment");
+  if (p.out_bf16) DCLIP_REQUIRE(p.ldcb % 4 == 0 && p.split_out_off % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 7) == 0, "out_bf16 alignment");
+  if (p.residual) DCLIP_REQUIRE(p.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0, "residual alignment");
+  if (p.bias) DCLIP_REQUIRE((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "bias alignment");
+  if (bn == 0) bn = p.N > 128 ? 256 : (p.N > 64 ? 128 : 64);
+  DCLIP_REQUIRE(bn == 256 || bn == 128 || bn == 64, "unsupported BLOCK_N %d", bn);
+  GemmPlan plan;
+  plan.p = p;
+  plan.bn = bn;
+  const uint64_t kcols = p.split_in ? 2ull * p.K : uint64_t(p.K);
+  plan.tmA = make_tmap_2d_bf16(op.A, p.M, kcols, op.lda, 128);
+  plan.tmB = make_tmap_2d_bf16(op.W, p.N, kcols, op.ldw, bn);
+  const int num_tiles = ((p.M + 127) / 128) * ((p.N + bn - 1) / bn);
+  plan.grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  if (max_ctas > 0 && plan.grid > max_ctas) plan.grid = max_ctas;
+  return plan;
+}
+
+inline void run_gemm(const GemmPlan& plan, cudaStream_t stream) {
+  switch (plan.bn) {
+    case 256: launch_gemm_bn<256>(plan, stream); break;
+    case 128: launch_gemm_bn<128>(plan, stream); break;
+    case 64: launch_gemm_bn<64>(plan, stream); break;
+    default: throw Error{"unsupported BLOCK_N"};
+  }
+}
+
+inline void launch_gemm(const GemmOperands& op, const GemmParams& p, cudaStream_t stream, int bn = 0, int max_ctas = 0) {
+  run_gemm(make_gemm_plan(op, p, bn, max_ctas), stream);
+}
+
+}  // namespace dclip
