@@ -1,0 +1,497 @@
+// Flash-attention forward for sm_100a (head_dim 64, non-causal), replacing the softmax(QK^T)V inside
+// nn.MultiheadAttention of the reference ViT block (segmentation/denseclip/models.py:287-289).
+//
+//   * one CTA = one (image, head, 256-query block): two 128-row query tiles share every K/V tile
+//   * S = Q K^T and O += P V run on tcgen05.mma (bf16 in, fp32 accumulate in TMEM); S and O never leave the SM
+//   * warp roles: warp 0 TMA producer (Q once, K/V 4-stage ring), warp 1 MMA issuer, warp 2 TMEM allocator,
+//     warps 4-7 / 8-11 = softmax warpgroups for query tile 0 / 1 (one thread per query row)
+//   * softmax: fp32 online softmax in the exp2 domain with the 1/sqrt(d) scale folded in; O stays in TMEM and is
+//     rescaled lazily (only when the running max grows by more than 2^8), P goes through swizzled smem as the
+//     A operand of the PV MMA; the two warpgroups ping-pong so MMA time hides behind the MUFU-bound softmax
+//   * the ragged tail (N = 2049 = 16*128 + 1) costs a 16-wide MMA, not a 17th full tile
+#pragma once
+#include "ptx.cuh"
+
+namespace dclip {
+
+struct AttnParams {
+  int B, H;
+  int Nq_total;  // rows in the Q tensor (TMA bound along tokens)
+  int q_start;   // first query row processed by this launch
+  int Nk;        // number of keys/values
+  int q_col0, k_col0, v_col0;  // column of head 0 inside a token row of the Q / K / V tensor
+  float scale_log2;            // head_dim^-0.5 * log2(e)
+  __nv_bfloat16* out;          // out[b][row][h*64 + d]
+  long long out_batch_stride;  // elements
+  int ldo;                     // elements
+};
+
+struct AttnCfg {
+  static constexpr int TQ = 128, TKV = 128, HD = 64, KV_STAGES = 4;
+  static constexpr int Q_OFF = 0;                               // 2 x 16 KB
+  static constexpr int K_OFF = 2 * 16384;                       // KV_STAGES x 16 KB
+  static constexpr int V_OFF = K_OFF + KV_STAGES * 16384;       // KV_STAGES x 16 KB
+  static constexpr int P_OFF = V_OFF + KV_STAGES * 16384;       // 2 x 32 KB
+  static constexpr int BAR_OFF = P_OFF + 2 * 32768;
+  static constexpr int NUM_BARS = 1 + 3 * KV_STAGES + 8;
+  static constexpr int SMEM_BYTES = BAR_OFF + NUM_BARS * 8 + 16;
+  static constexpr int THREADS = 384;
+  static constexpr int TMEM_COLS = 512;  // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
+};
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// One KV tile of the online softmax for one query row (= one thread): S (NC columns, fp32, TMEM) -> P (bf16, smem).
+// NC = 128 for regular tiles, 32 for a short ragged tail.  `valid` < NC masks the trailing columns.
+template <int NC>
+__device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint8_t* sProw, int r, int lane, int valid,
+                                                  bool first, float sc, float& m_used, float& l, uint64_t* s_free_bar,
+                                                  uint64_t* o_done_bar, uint32_t o_done_parity) {
+  uint32_t su[NC];
+#pragma unroll
+  for (int c = 0; c < NC / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, reinterpret_cast<uint32_t(&)[32]>(su[c * 32]));
+  tmem_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(s_free_bar);
+  if (valid < NC) {
+#pragma unroll
+    for (int e = 0; e < NC; ++e)
+      if (e >= valid) su[e] = 0xff800000u;  // -inf
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < NC; e += 8) {
+    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(su[e]), __uint_as_float(su[e + 1])));
+    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(su[e + 2]), __uint_as_float(su[e + 3])));
+    mx2 = fmaxf(mx2, fmaxf(__uint_as_float(su[e + 4]), __uint_as_float(su[e + 5])));
+    mx3 = fmaxf(mx3, fmaxf(__uint_as_float(su[e + 6]), __uint_as_float(su[e + 7])));
+  }
+  const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+  // lazy rescale: keep the old reference max unless it grew by more than 2^8 (first tile: m_used = -inf -> always)
+  const bool need = (m_new - m_used) * sc > 8.0f;
+  const bool rescale = __any_sync(0xffffffffu, need);
+  float alpha = 1.0f;
+  if (rescale) {
+    alpha = ex2_approx((m_used - m_new) * sc);
+    m_used = m_new;
+    l *= alpha;
+  }
+  // P = exp2(S * sc - m * sc): all exponentials first (registers), so the wait for the previous PV below is
+  // normally already satisfied when we get there
+  const uint64_t sc2 = pack_f32x2(sc, sc);
+  const float nmc = -m_used * sc;
+  const uint64_t nmc2 = pack_f32x2(nmc, nmc);
+  uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
+  uint4 pk[NC / 8];
+#pragma unroll
+  for (int c16 = 0; c16 < NC / 8; ++c16) {
+    float pv[8];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      const uint64_t t = fma_f32x2(pack_f32x2(__uint_as_float(su[c16 * 8 + e]), __uint_as_float(su[c16 * 8 + e + 1])), sc2, nmc2);
+      float t0, t1;
+      unpack_f32x2(t, t0, t1);
+      pv[e] = ex2_approx(t0);
+      pv[e + 1] = ex2_approx(t1);
+    }
+    acc0 = add_f32x2(acc0, add_f32x2(pack_f32x2(pv[0], pv[1]), pack_f32x2(pv[2], pv[3])));
+    acc1 = add_f32x2(acc1, add_f32x2(pack_f32x2(pv[4], pv[5]), pack_f32x2(pv[6], pv[7])));
+    pk[c16] = make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
+                         pack_bf16x2(pv[6], pv[7]));
+  }
+  float a0, a1, a2, a3;
+  unpack_f32x2(acc0, a0, a1);
+  unpack_f32x2(acc1, a2, a3);
+  l += (a0 + a1) + (a2 + a3);
+  // PV of the previous tile must be done before P is overwritten or O is touched
+  if (!first) {
+    mbar_wait(o_done_bar, o_done_parity);
+    tc_fence_after();
+    if (rescale) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tO + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+        tmem_st_32x32b_x32(tO + c * 32, o);
+      }
+      tmem_wait_st();
+    }
+  }
+#pragma unroll
+  for (int c16 = 0; c16 < NC / 8; ++c16)
+    *reinterpret_cast<uint4*>(sProw + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4)) = pk[c16];
+}
+
+__global__ void __launch_bounds__(AttnCfg::THREADS, 1)
+attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using Cfg = AttnCfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = k_full + Cfg::KV_STAGES;
+  uint64_t* kv_empty = v_full + Cfg::KV_STAGES;
+  uint64_t* s_full = kv_empty + Cfg::KV_STAGES;  // [2]  MMA  -> softmax : S tile ready in TMEM
+  uint64_t* s_free = s_full + 2;                 // [2]  softmax -> MMA : S tile copied to registers
+  uint64_t* p_ready = s_free + 2;                // [2]  softmax -> MMA : P tile in smem (and O rescaled)
+  uint64_t* o_done = p_ready + 2;                // [2]  MMA  -> softmax : PV accumulate finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqb = (p.Nq_total - p.q_start + 2 * Cfg::TQ - 1) / (2 * Cfg::TQ);
+  const int qb = blockIdx.x % nqb;
+  const int h = (blockIdx.x / nqb) % p.H;
+  const int b = blockIdx.x / (nqb * p.H);
+  const int q_row0 = p.q_start + qb * 2 * Cfg::TQ;
+  const int T = (p.Nk + Cfg::TKV - 1) / Cfg::TKV;
+  const int last_valid = p.Nk - (T - 1) * Cfg::TKV;     // valid columns of the last KV tile (1..128)
+  const int last_cols16 = (last_valid + 15) & ~15;      // MMA extent of the last KV tile
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("dclip attn: dynamic smem base not 1024B aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < Cfg::KV_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&o_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    setmaxnreg_dec<80>();
+    if (warp == 0) {
+      // ------------------------------- TMA producer -------------------------------
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * 16384);
+        tma_load_3d(smem + Cfg::Q_OFF, &tmQ, q_full, p.q_col0 + h * Cfg::HD, q_row0, b);
+        tma_load_3d(smem + Cfg::Q_OFF + 16384, &tmQ, q_full, p.q_col0 + h * Cfg::HD, q_row0 + Cfg::TQ, b);
+        for (int j = 0; j < T; ++j) {
+          const int s = j % Cfg::KV_STAGES;
+          const uint32_t ph = (j / Cfg::KV_STAGES) & 1;
+          mbar_wait(&kv_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[s], 16384);
+          tma_load_3d(smem + Cfg::K_OFF + s * 16384, &tmK, &k_full[s], p.k_col0 + h * Cfg::HD, j * Cfg::TKV, b);
+          mbar_arrive_expect_tx(&v_full[s], 16384);
+          tma_load_3d(smem + Cfg::V_OFF + s * 16384, &tmV, &v_full[s], p.v_col0 + h * Cfg::HD, j * Cfg::TKV, b);
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------- MMA issuer ---------------------------------
+      const uint32_t sQ = smem_u32(smem + Cfg::Q_OFF), sK = smem_u32(smem + Cfg::K_OFF);
+      const uint32_t sV = smem_u32(smem + Cfg::V_OFF), sP = smem_u32(smem + Cfg::P_OFF);
+      auto issue_qk = [&](int i, int stage, int ncols16) {
+        const uint32_t idesc = make_idesc_bf16(128, ncols16);
+        const uint32_t a = sQ + i * 16384, bb = sK + stage * 16384;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss_f16(tmem_base + i * 128, make_smem_desc_sw128(a + ks * 32, 16, 1024),
+                      make_smem_desc_sw128(bb + ks * 32, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+        umma_commit(&s_full[i]);
+      };
+      auto issue_pv = [&](int i, int stage, int ncols16, bool acc) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major: head_dim contiguous
+        const uint32_t a = sP + i * 32768, bb = sV + stage * 16384;
+        for (int ks = 0; ks < ncols16 / 16; ++ks)
+          umma_ss_f16(tmem_base + 256 + i * 64, make_smem_desc_sw128(a + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(bb + ks * 2048, 16, 1024), idesc, (acc || ks > 0) ? 1u : 0u);
+        umma_commit(&o_done[i]);
+      };
+      // Issue order: S tiles are produced two KV tiles ahead of their use (S_i(j+2) is issued as soon as warpgroup i
+      // has pulled S_i(j+1) into registers), so the softmax warpgroups never wait on QK^T; PV(i,j) goes out as soon
+      // as P_i(j) is in smem.  The two warpgroups may drift by up to a tile without blocking each other.
+      auto ncols_of = [&](int j) { return (j + 1 == T) ? last_cols16 : 128; };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      if (lane == 0) {
+        issue_qk(0, 0, ncols_of(0));
+        issue_qk(1, 0, ncols_of(0));
+      }
+      __syncwarp();
+      if (T > 1) {
+        mbar_wait(&k_full[1 % Cfg::KV_STAGES], (1 / Cfg::KV_STAGES) & 1);
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(&s_free[i], 0);
+          tc_fence_after();
+          if (lane == 0) issue_qk(i, 1 % Cfg::KV_STAGES, ncols_of(1));
+          __syncwarp();
+        }
+      }
+      for (int j = 0; j < T; ++j) {
+        const int s = j % Cfg::KV_STAGES;
+        mbar_wait(&v_full[s], (j / Cfg::KV_STAGES) & 1);
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(&p_ready[i], j & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            issue_pv(i, s, ncols_of(j), j > 0);
+            if (i == 1) umma_commit(&kv_empty[s]);
+          }
+          __syncwarp();
+          if (j + 2 < T) {
+            const int s2 = (j + 2) % Cfg::KV_STAGES;
+            if (i == 0) mbar_wait(&k_full[s2], ((j + 2) / Cfg::KV_STAGES) & 1);
+            mbar_wait(&s_free[i], (j + 1) & 1);
+            tc_fence_after();
+            if (lane == 0) issue_qk(i, s2, ncols_of(j + 2));
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------- softmax warpgroups --------------------------
+    setmaxnreg_inc<208>();
+    const int i = (warp - 4) >> 2;  // query tile
+    const int q = warp & 3;         // TMEM lane quarter
+    const int r = q * 32 + lane;    // row inside the tile
+    const uint32_t lane_off = uint32_t(q * 32) << 16;
+    const uint32_t tS = tmem_base + i * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + i * 64 + lane_off;
+    uint8_t* sProw = smem + Cfg::P_OFF + i * 32768 + (r >> 3) * 1024 + (r & 7) * 128;
+    const float sc = p.scale_log2;
+    float m_used = -INFINITY, l = 0.f;
+
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(&s_full[i], j & 1);
+      tc_fence_after();
+      const int valid = (j + 1 == T) ? last_valid : 128;
+      if (valid > 32)
+        attn_softmax_tile<128>(tS, tO, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1);
+      else
+        attn_softmax_tile<32>(tS, tO, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[i]);
+    }
+
+    // ------------------------------- output ---------------------------------------
+    mbar_wait(&o_done[i], (T - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    const int row = q_row0 + i * Cfg::TQ + r;
+    __nv_bfloat16* orow = p.out + (long long)b * p.out_batch_stride + (long long)row * p.ldo + h * Cfg::HD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tO + c * 32, o);
+      tmem_wait_ld();
+      if (row < p.Nq_total) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          const uint4 pk = make_uint4(pack_bf16x2(__uint_as_float(o[e]) * inv, __uint_as_float(o[e + 1]) * inv),
+                                      pack_bf16x2(__uint_as_float(o[e + 2]) * inv, __uint_as_float(o[e + 3]) * inv),
+                                      pack_bf16x2(__uint_as_float(o[e + 4]) * inv, __uint_as_float(o[e + 5]) * inv),
+                                      pack_bf16x2(__uint_as_float(o[e + 6]) * inv, __uint_as_float(o[e + 7]) * inv));
+          *reinterpret_cast<uint4*>(orow + c * 32 + e) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Few-query attention on CUDA cores (fp32 math): one CTA per (batch, head, query).  Used for the CLS query of the
+// ViT (so the tensor-core kernel sees 8 aligned 256-row blocks instead of 8 + a 1-row block), for the
+// ContextDecoder's 19-query self/cross attention (models.py:328-344) and for the causal 22-token text tower
+// (models.py:836-842).  Phase 1: thread-per-key dot products -> smem scores; block softmax; phase 2: column-parallel PV.
+// ---------------------------------------------------------------------------------------------------------
+struct SmallAttnParams {
+  const void* q; const void* k; const void* v;  // bf16 (is_f32 = 0) or fp32 (is_f32 = 1); [B][N][ld] token-major
+  int is_f32;
+  int B, H, Nk;
+  int q_first, q_count;        // query rows [q_first, q_first + q_count) are computed
+  int ldq, ldk, ldv;           // elements per token row
+  long long q_bs, k_bs, v_bs;  // batch strides (elements)
+  int q_col0, k_col0, v_col0;
+  float scale;                 // head_dim^-0.5 (applied to the logits)
+  int causal;                  // 1: key j allowed iff j <= query index
+  void* out; int out_f32; int ldo; long long out_bs;  // out[b][row][h*64 + d]
+  int out_split_off;           // > 0 (bf16 out only): also write lo = bf16(v - hi) at this column offset
+};
+
+__device__ __forceinline__ float ld_elem(const void* base, int is_f32, long long idx) {
+  return is_f32 ? reinterpret_cast<const float*>(base)[idx] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+
+// dynamic smem: Nk floats (scores) + 64 (q) + 8*64 (partial O) + 16 (reduction scratch)
+__global__ void __launch_bounds__(256) attn_small_kernel(const SmallAttnParams p) {
+  extern __shared__ float sm[];
+  float* sc = sm;
+  float* sq = sm + p.Nk;
+  float* so = sq + 64;
+  float* red = so + 512;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qi = p.q_first + blockIdx.x % p.q_count;
+  const int h = (blockIdx.x / p.q_count) % p.H;
+  const int b = blockIdx.x / (p.q_count * p.H);
+  const int nk = p.causal ? min(p.Nk, qi + 1) : p.Nk;
+  if (tid < 64) sq[tid] = ld_elem(p.q, p.is_f32, b * p.q_bs + (long long)qi * p.ldq + p.q_col0 + h * 64 + tid) * p.scale;
+  __syncthreads();
+  // phase 1: scores
+  float mx = -INFINITY;
+  for (int j = tid; j < nk; j += 256) {
+    const long long koff = b * p.k_bs + (long long)j * p.ldk + p.k_col0 + h * 64;
+    float s = 0.f;
+    if (p.is_f32) {
+      const float4* kp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.k) + koff);
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const float4 kv = kp[d];
+        s += sq[4 * d] * kv.x + sq[4 * d + 1] * kv.y + sq[4 * d + 2] * kv.z + sq[4 * d + 3] * kv.w;
+      }
+    } else {
+      const uint4* kp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.k) + koff);
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const uint4 kv = kp[d];
+        const uint32_t w[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          s += sq[8 * d + 2 * e] * __uint_as_float(w[e] << 16) + sq[8 * d + 2 * e + 1] * __uint_as_float(w[e] & 0xffff0000u);
+      }
+    }
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  float sum = 0.f;
+  for (int j = tid; j < nk; j += 256) {
+    const float e = __expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[8 + warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[8 + w];
+  // phase 2: O[d] = sum_j p_j V[j][d]; thread (g, d8) covers keys j = g, g+32, ... and 8 consecutive dims
+  // (one 16 B / 32 B vector load per key; 4 keys in flight per thread)
+  const int d8 = tid & 7, g = tid >> 3;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const long long vbase = b * p.v_bs + p.v_col0 + h * 64 + d8 * 8;
+  for (int j0 = g; j0 < nk; j0 += 128) {
+    float pj[4];
+    uint4 raw[4][2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u;
+      pj[u] = j < nk ? sc[j] : 0.f;
+      const long long voff = vbase + (long long)(j < nk ? j : j0) * p.ldv;
+      if (p.is_f32) {
+        const uint4* vp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.v) + voff);
+        raw[u][0] = vp[0];
+        raw[u][1] = vp[1];
+      } else {
+        raw[u][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.v) + voff);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p.is_f32) {
+        const uint32_t w[8] = {raw[u][0].x, raw[u][0].y, raw[u][0].z, raw[u][0].w, raw[u][1].x, raw[u][1].y, raw[u][1].z, raw[u][1].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += pj[u] * __uint_as_float(w[e]);
+      } else {
+        const uint32_t w[4] = {raw[u][0].x, raw[u][0].y, raw[u][0].z, raw[u][0].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] += pj[u] * __uint_as_float(w[e] << 16);
+          acc[2 * e + 1] += pj[u] * __uint_as_float(w[e] & 0xffff0000u);
+        }
+      }
+    }
+  }
+  // reduce the 32 key groups: shuffle across the 4 groups inside a warp, then smem across the 8 warps
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) so[warp * 64 + lane * 8 + e] = acc[e];
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) o += so[w * 64 + tid];
+    o /= sum;
+    const long long ooff = b * p.out_bs + (long long)qi * p.ldo + h * 64 + tid;
+    if (p.out_f32) {
+      reinterpret_cast<float*>(p.out)[ooff] = o;
+    } else {
+      const __nv_bfloat16 hi = __float2bfloat16(o);
+      reinterpret_cast<__nv_bfloat16*>(p.out)[ooff] = hi;
+      if (p.out_split_off > 0)
+        reinterpret_cast<__nv_bfloat16*>(p.out)[ooff + p.out_split_off] = __float2bfloat16(o - __bfloat162float(hi));
+    }
+  }
+}
+
+}  // namespace dclip

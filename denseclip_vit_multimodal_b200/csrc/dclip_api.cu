@@ -1,0 +1,354 @@
+// C ABI of libdenseclip_b200.so (see include/denseclip_b200.h).  Thin, exception-free boundary over the kernels in
+// gemm_tcgen05.cuh / attn_tcgen05.cuh / rowwise.cuh, plus the CLIPVisionTransformer forward as one native call.
+#include "../../include/denseclip_b200.h"
+
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "host_utils.cuh"
+#include "rowwise.cuh"
+#include "vit_encoder.cuh"
+
+using namespace dclip;
+
+struct dclip_handle_s {
+  int device = 0;
+  std::string err;
+  long long launches = 0;
+  // plan caches: tensor maps are encoded once per distinct argument set
+  std::map<std::string, GemmPlan> gemm_plans;
+  std::map<std::string, AttnPlan> attn_plans;
+};
+
+struct dclip_vit_s {
+  dclip_handle_t h;
+  VitEncoder enc;
+};
+
+static thread_local std::string g_create_err;
+
+template <class F>
+static int guarded(dclip_handle_t h, F&& f) {
+  try {
+    if (!h) throw Error{"null handle"};
+    int cur = -1;
+    DCLIP_CHECK_CUDA(cudaGetDevice(&cur));
+    if (cur != h->device) DCLIP_CHECK_CUDA(cudaSetDevice(h->device));
+    f();
+    return 0;
+  } catch (const Error& e) {
+    if (h) h->err = e.msg; else g_create_err = e.msg;
+    return 1;
+  } catch (const std::exception& e) {
+    if (h) h->err = e.what(); else g_create_err = e.what();
+    return 2;
+  }
+}
+
+template <class T>
+static std::string key_of(const T& v) {
+  return std::string(reinterpret_cast<const char*>(&v), sizeof(T));
+}
+
+static void check_launch(dclip_handle_t h, int n = 1) {
+  DCLIP_CHECK_CUDA(cudaGetLastError());
+  h->launches += n;
+}
+
+extern "C" {
+
+int dclip_abi_version(void) { return DCLIP_ABI_VERSION; }
+
+int dclip_create(int device, dclip_handle_t* out) {
+  try {
+    if (!out) throw Error{"dclip_create: out is null"};
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) throw Error{std::string("dclip_create: no CUDA device (") + cudaGetErrorString(e) + ")"};
+    if (device < 0 || device >= n) throw Error{"dclip_create: bad device index"};
+    cudaDeviceProp prop;
+    DCLIP_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+      char buf[160];
+      snprintf(buf, sizeof(buf), "dclip_create: device %d is sm_%d%d; this library contains sm_100a code only", device,
+               prop.major, prop.minor);
+      throw Error{buf};
+    }
+    DCLIP_CHECK_CUDA(cudaSetDevice(device));
+    get_encode_fn();
+    auto* h = new dclip_handle_s;
+    h->device = device;
+    *out = h;
+    return 0;
+  } catch (const Error& e) {
+    g_create_err = e.msg;
+    return 1;
+  }
+}
+
+int dclip_destroy(dclip_handle_t h) {
+  delete h;
+  return 0;
+}
+
+const char* dclip_last_error(dclip_handle_t h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+long long dclip_launch_count(dclip_handle_t h) { return h ? h->launches : 0; }
+int dclip_reset_launch_count(dclip_handle_t h) {
+  if (h) h->launches = 0;
+  return 0;
+}
+
+int dclip_gemm(dclip_handle_t h, const dclip_gemm_args* a, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(a != nullptr, "null args");
+    const std::string key = key_of(*a);
+    auto it = h->gemm_plans.find(key);
+    if (it == h->gemm_plans.end()) {
+      GemmOperands op{static_cast<const __nv_bfloat16*>(a->A), int(a->lda), static_cast<const __nv_bfloat16*>(a->W), int(a->ldw)};
+      op.a_bs = a->a_bs; op.conv_B = a->conv_B; op.conv_gh = a->conv_gh;
+      GemmParams p{};
+      p.M = a->M; p.N = a->N; p.K = a->K; p.split_in = a->split_in;
+      p.bias = a->bias; p.act = a->act; p.out_scale = a->out_scale;
+      p.residual = a->residual; p.ldr = int(a->ldr); p.res_mod = a->res_mod;
+      p.remap_P = a->remap_P; p.remap_Nt = a->remap_Nt;
+      p.out_f32 = a->out_f32; p.ldc = int(a->ldc);
+      p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); p.ldcb = int(a->ldcb);
+      p.split_out = a->split_out; p.split_out_off = int(a->split_out_off);
+      if (a->conv_C > 0) {
+        p.conv_C = a->conv_C; p.conv_gw = a->conv_gw;
+        p.conv_tiles_per_img = a->conv_gh * a->conv_gw / 128;
+      }
+      DCLIP_REQUIRE(p.out_f32 || p.out_bf16, "GEMM needs at least one output");
+      if (h->gemm_plans.size() > 4096) h->gemm_plans.clear();
+      it = h->gemm_plans.emplace(key, make_gemm_plan(op, p, a->block_n)).first;
+    }
+    run_gemm(it->second, static_cast<cudaStream_t>(stream));
+    h->launches += 1;
+  });
+}
+
+int dclip_layernorm(dclip_handle_t h, const float* x, long long ldx, const float* gamma, const float* beta, float eps,
+                    int M, int D, float* out_f32, long long ldo, void* out_bf16, long long ldb, int split,
+                    long long split_off, void* stream) {
+  return guarded(h, [&] {
+    LayerNormParams p{x, ldx, gamma, beta, eps, M, D, out_f32, ldo, static_cast<__nv_bfloat16*>(out_bf16), ldb, split, int(split_off)};
+    launch_layernorm(p, static_cast<cudaStream_t>(stream));
+    check_launch(h);
+  });
+}
+
+int dclip_cast_bf16(dclip_handle_t h, const float* x, long long ldx, void* out, long long ldo, int rows, int cols,
+                    int split, long long split_off, float scale, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(cols % 2 == 0 && ldx % 2 == 0 && ldo % 2 == 0 && split_off % 2 == 0, "cast: even cols/ld required");
+    CastParams p{x, ldx, static_cast<__nv_bfloat16*>(out), ldo, rows, cols, split, int(split_off), scale};
+    const long long total = (long long)rows * (cols / 2);
+    const int grid = int(std::min<long long>((total + 255) / 256, 148 * 16));
+    cast_bf16_kernel<<<std::max(grid, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    check_launch(h);
+  });
+}
+
+int dclip_attention(dclip_handle_t h, const void* q, const void* k, const void* v, long long ldq, long long ldk,
+                    long long ldv, long long q_bs, long long k_bs, long long v_bs, int q_col0, int k_col0, int v_col0,
+                    int B, int H, int Nq, int q_start, int Nk, float scale, void* out, long long ldo, long long out_bs,
+                    void* stream) {
+  return guarded(h, [&] {
+    AttnOperands op{static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v),
+                    int(ldq), int(ldk), int(ldv), q_bs, k_bs, v_bs, Nq};
+    AttnParams p{};
+    p.B = B; p.H = H; p.Nq_total = Nq; p.q_start = q_start; p.Nk = Nk;
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.out = static_cast<__nv_bfloat16*>(out); p.out_batch_stride = out_bs; p.ldo = int(ldo);
+    const std::string key = key_of(op) + key_of(p);
+    auto it = h->attn_plans.find(key);
+    if (it == h->attn_plans.end()) {
+      if (h->attn_plans.size() > 1024) h->attn_plans.clear();
+      it = h->attn_plans.emplace(key, make_attn_plan(op, p)).first;
+    }
+    run_attn(it->second, static_cast<cudaStream_t>(stream));
+    h->launches += 1;
+  });
+}
+
+int dclip_attention_small(dclip_handle_t h, const void* q, const void* k, const void* v, int is_f32, long long ldq,
+                          long long ldk, long long ldv, long long q_bs, long long k_bs, long long v_bs, int q_col0,
+                          int k_col0, int v_col0, int B, int H, int q_first, int q_count, int Nk, float scale, int causal,
+                          void* out, int out_f32, long long ldo, long long out_bs, long long out_split_off, void* stream) {
+  return guarded(h, [&] {
+    SmallAttnParams p{};
+    p.q = q; p.k = k; p.v = v; p.is_f32 = is_f32; p.B = B; p.H = H; p.Nk = Nk; p.q_first = q_first; p.q_count = q_count;
+    p.ldq = int(ldq); p.ldk = int(ldk); p.ldv = int(ldv); p.q_bs = q_bs; p.k_bs = k_bs; p.v_bs = v_bs;
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0; p.scale = scale; p.causal = causal;
+    p.out = out; p.out_f32 = out_f32; p.ldo = int(ldo); p.out_bs = out_bs; p.out_split_off = int(out_split_off);
+    const int align = is_f32 ? 4 : 8;
+    DCLIP_REQUIRE(ldk % align == 0 && ldv % align == 0 && k_col0 % align == 0 && v_col0 % align == 0 && k_bs % align == 0 &&
+                      v_bs % align == 0, "small attention: K/V rows must be 16B aligned");
+    run_attn_small(p, static_cast<cudaStream_t>(stream));
+    h->launches += 1;
+  });
+}
+
+int dclip_im2col_patches(dclip_handle_t h, const float* img, int B, int H, int W, int ps, void* out, long long lda,
+                         int split, long long split_off, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(ps > 0 && ps % 2 == 0 && H >= ps && W >= ps, "im2col: even patch size <= image required");
+    Im2colParams p{img, static_cast<__nv_bfloat16*>(out), lda, B, H, W, ps, H / ps, W / ps, split, int(split_off)};
+    launch_im2col(p, static_cast<cudaStream_t>(stream));
+    check_launch(h);
+  });
+}
+
+int dclip_posemb_interp(dclip_handle_t h, const float* pos, int g0, int gh, int gw, int D, float* out, void* stream) {
+  return guarded(h, [&] {
+    posemb_interp_kernel<<<1 + gh * gw, 256, 0, static_cast<cudaStream_t>(stream)>>>(pos, out, g0, gh, gw, D);
+    check_launch(h);
+  });
+}
+
+int dclip_tap_nchw(dclip_handle_t h, const float* tokens, int B, int Ntok, int D, float* out_nchw, void* stream) {
+  return guarded(h, [&] {
+    launch_tap_nchw(tokens, out_nchw, B, Ntok, D, static_cast<cudaStream_t>(stream));
+    check_launch(h);
+  });
+}
+
+int dclip_nchw_to_tokens(dclip_handle_t h, const float* in_nchw, int B, int C, int P, float* out_f32, void* out_bf16,
+                         long long ld, long long out_bs, int row_off, void* stream) {
+  return guarded(h, [&] {
+    dim3 grid((P + 31) / 32, (C + 31) / 32, B);
+    nchw_to_tokens_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_nchw, out_f32, static_cast<__nv_bfloat16*>(out_bf16),
+                                                                               C, P, ld, out_bs, row_off);
+    check_launch(h);
+  });
+}
+
+int dclip_token_mean(dclip_handle_t h, const float* x, int B, int row0, int P, long long ld, long long bs, int D,
+                     float* out, void* stream) {
+  return guarded(h, [&] {
+    dim3 grid((D + 31) / 32, B);
+    token_mean_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, row0, P, ld, bs, D);
+    check_launch(h);
+  });
+}
+
+int dclip_score_map(dclip_handle_t h, const float* vis, long long ld, long long bs, int row0, const float* text, int B,
+                    int K, int C, int P, float eps, float* score, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(C % 32 == 0 && C <= 1024, "score map: C=%d must be a multiple of 32 and <= 1024", C);
+    const size_t smem = size_t(K) * C * 4;
+    DCLIP_REQUIRE(smem <= 200 * 1024, "score map: K*C too large for shared memory");
+    static bool attr = false;
+    if (!attr) {
+      DCLIP_CHECK_CUDA(cudaFuncSetAttribute(score_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    ScoreParams p{vis, ld, bs, row0, text, score, B, K, C, P, eps};
+    dim3 grid(std::min((P + 7) / 8, 64), B);
+    score_map_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    check_launch(h);
+  });
+}
+
+int dclip_upsample_bilinear(dclip_handle_t h, const float* in, int in_nchw, long long ldi, long long in_bs, int B, int C,
+                            int hh, int ww, int H, int W, float* out, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(W % 4 == 0, "upsample: output width must be a multiple of 4");
+    UpsampleParams p{in, in_nchw, ldi, in_bs, out, B, C, hh, ww, H, W};
+    const long long total = (long long)B * C * H * (W / 4);
+    const int grid = int(std::min<long long>((total + 255) / 256, 148 * 32));
+    upsample_bilinear_kernel<<<std::max(grid, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    check_launch(h);
+  });
+}
+
+int dclip_gamma_residual(dclip_handle_t h, const float* a, const float* gamma, const float* d, float* out, long long n,
+                         int C, void* stream) {
+  return guarded(h, [&] {
+    gamma_residual_kernel<<<int((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, gamma, d, out, n, C);
+    check_launch(h);
+  });
+}
+
+int dclip_conv3x3_gather(dclip_handle_t h, const void* in, int in_f32, long long ld, long long bs, int row0, int B, int hh,
+                         int ww, int C, void* out, long long ldo, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(C % 2 == 0 && ldo % 2 == 0, "conv gather: even C required");
+    Conv3x3GatherParams p{in, in_f32, ld, bs, row0, B, hh, ww, C, static_cast<__nv_bfloat16*>(out), ldo};
+    const long long total = (long long)B * hh * ww * 9 * (C / 2);
+    const int grid = int(std::min<long long>((total + 255) / 256, 148 * 32));
+    conv3x3_gather_kernel<<<std::max(grid, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    check_launch(h);
+  });
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ViT encoder
+// ------------------------------------------------------------------------------------------------------------
+int dclip_vit_create(dclip_handle_t h, const dclip_vit_config* cfg, dclip_vit_t* out) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(cfg && out, "null argument");
+    auto v = std::make_unique<dclip_vit_s>();
+    v->h = h;
+    v->enc.configure(VitConfig{cfg->width, cfg->layers, cfg->heads, cfg->patch_size, cfg->grid0, cfg->precise});
+    *out = v.release();
+  });
+}
+
+int dclip_vit_destroy(dclip_vit_t v) {
+  delete v;
+  return 0;
+}
+
+int dclip_vit_set_weights(dclip_vit_t v, const dclip_vit_weights* w) {
+  if (!v) return 1;
+  return guarded(v->h, [&] {
+    DCLIP_REQUIRE(w != nullptr, "null weights");
+    VitWeights& dst = v->enc.weights;
+    const int L = v->enc.cfg.layers;
+    dst.conv1_w = static_cast<const __nv_bfloat16*>(w->conv1_w);
+    dst.class_embedding = w->class_embedding;
+    dst.positional_embedding = w->positional_embedding;
+    dst.ln_pre_g = w->ln_pre_g; dst.ln_pre_b = w->ln_pre_b; dst.ln_post_g = w->ln_post_g; dst.ln_post_b = w->ln_post_b;
+    dst.layers.resize(L);
+    for (int i = 0; i < L; ++i) {
+      VitLayerWeights& l = dst.layers[i];
+      l.ln1_g = w->ln1_g[i]; l.ln1_b = w->ln1_b[i]; l.ln2_g = w->ln2_g[i]; l.ln2_b = w->ln2_b[i];
+      l.in_proj_w = static_cast<const __nv_bfloat16*>(w->in_proj_w[i]); l.in_proj_b = w->in_proj_b[i];
+      l.out_proj_w = static_cast<const __nv_bfloat16*>(w->out_proj_w[i]); l.out_proj_b = w->out_proj_b[i];
+      l.fc_w = static_cast<const __nv_bfloat16*>(w->fc_w[i]); l.fc_b = w->fc_b[i];
+      l.proj_w = static_cast<const __nv_bfloat16*>(w->proj_w[i]); l.proj_b = w->proj_b[i];
+    }
+    v->enc.invalidate_plans();
+  });
+}
+
+int dclip_vit_workspace_bytes(dclip_vit_t v, int B, int H, int W, size_t* bytes) {
+  if (!v) return 1;
+  return guarded(v->h, [&] {
+    DCLIP_REQUIRE(bytes != nullptr, "null argument");
+    *bytes = v->enc.workspace_bytes(B, H, W);
+  });
+}
+
+int dclip_vit_forward(dclip_vit_t v, const float* img, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                      const dclip_vit_outputs* outs, void* stream) {
+  if (!v) return 1;
+  return guarded(v->h, [&] {
+    DCLIP_REQUIRE(outs != nullptr && img != nullptr && workspace != nullptr, "null argument");
+    VitOutputs o;
+    o.last_tokens_f32 = outs->last_tokens_f32;
+    for (int i = 0; i < outs->n_taps; ++i) {
+      VitTap t;
+      t.layer = outs->tap_layers[i];
+      t.nchw = outs->taps_nchw ? outs->taps_nchw[i] : nullptr;
+      t.tokens_bf16 = outs->taps_tokens_bf16 ? static_cast<__nv_bfloat16*>(outs->taps_tokens_bf16[i]) : nullptr;
+      o.taps.push_back(t);
+    }
+    v->h->launches += v->enc.forward(img, B, H, W, workspace, workspace_bytes, o, static_cast<cudaStream_t>(stream));
+  });
+}
+
+}  // extern "C"

@@ -39,6 +39,9 @@ struct GemmParams {
   int split_out;          // 1: also write lo = bf16(v - hi) at column offset split_out_off
   int split_out_off;
   float out_scale;        // applied after activation, before residual (1.0f default)
+  // implicit 3x3 / pad-1 convolution (conv_C > 0): A is a token-major image [B][gh][gw][C(x2 if split_in)] read through a
+  // 4D tensor map; K = 9*C ordered (ky, kx, c); M = B*gh*gw with 128-pixel tiles that never straddle an image.
+  int conv_C, conv_gw, conv_tiles_per_img;
 };
 
 // Compile-time epilogue specialisation. ACT < 0 / FLAGS < 0 select the generic (runtime-checked) epilogue.
@@ -141,7 +144,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             b_col = (seg == 2 ? p.K : 0) + off;
           }
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, &full_bar[stage], a_col, m_blk * BM);
+          if (p.conv_C > 0) {
+            const int kc = kb % kseg;                     // k-block inside the (ky, kx, c) K range
+            const int cpb = p.conv_C / BK;                // k-blocks per filter tap
+            const int tap = kc / cpb, c0 = (kc - tap * cpb) * BK + (a_col >= p.K ? p.conv_C : 0);
+            const int img = m_blk / p.conv_tiles_per_img, p0 = (m_blk - img * p.conv_tiles_per_img) * BM;
+            const int y0 = p0 / p.conv_gw, x0 = p0 - y0 * p.conv_gw;
+            tma_load_4d(sa, &tmA, &full_bar[stage], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], a_col, m_blk * BM);
+          }
           tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], b_col, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

@@ -10,6 +10,7 @@
 #include <mutex>
 #include <string>
 
+#include "attn_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 
 namespace dclip {
@@ -105,6 +106,9 @@ struct GemmOperands {
   int lda;  // elements
   const __nv_bfloat16* W;
   int ldw;
+  // implicit-conv mode (GemmParams::conv_C > 0): A is [B][row0 + gh*gw][lda] token-major with batch stride a_bs
+  long long a_bs = 0;
+  int conv_B = 0, conv_gh = 0;
 };
 
 // A GEMM launch with its tensor maps pre-encoded (cuTensorMapEncodeTiled is a driver call; plans are built once per
@@ -157,7 +161,19 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
   plan.p = p;
   plan.bn = bn;
   const uint64_t kcols = p.split_in ? 2ull * p.K : uint64_t(p.K);
-  plan.tmA = make_tmap_2d_bf16(op.A, p.M, kcols, op.lda, 128);
+  if (p.conv_C > 0) {
+    const int gw = p.conv_gw, gh = op.conv_gh;
+    DCLIP_REQUIRE(p.conv_C % 64 == 0 && p.K == 9 * p.conv_C, "implicit conv: C %% 64 == 0 and K == 9*C required");
+    DCLIP_REQUIRE((gh * gw) % 128 == 0 && (128 % gw == 0 || gw % 128 == 0), "implicit conv: grid %dx%d not tileable by 128 pixels", gh, gw);
+    DCLIP_REQUIRE(p.M == op.conv_B * gh * gw && p.conv_tiles_per_img == gh * gw / 128, "implicit conv: inconsistent M");
+    const uint32_t bw = gw < 128 ? gw : 128, bh = 128 / bw;
+    uint64_t dims[4] = {uint64_t(p.conv_C) * (p.split_in ? 2 : 1), uint64_t(gw), uint64_t(gh), uint64_t(op.conv_B)};
+    uint64_t str[3] = {uint64_t(op.lda) * 2, uint64_t(op.lda) * 2 * gw, uint64_t(op.a_bs) * 2};
+    uint32_t box[4] = {64, bw, bh, 1};
+    plan.tmA = make_tmap_bf16(op.A, 4, dims, str, box);
+  } else {
+    plan.tmA = make_tmap_2d_bf16(op.A, p.M, kcols, op.lda, 128);
+  }
   plan.tmB = make_tmap_2d_bf16(op.W, p.N, kcols, op.ldw, bn);
   const int num_tiles = ((p.M + 127) / 128) * ((p.N + bn - 1) / bn);
   plan.grid = num_tiles < sm_count() ? num_tiles : sm_count();
@@ -176,6 +192,61 @@ inline void run_gemm(const GemmPlan& plan, cudaStream_t stream) {
 
 inline void launch_gemm(const GemmOperands& op, const GemmParams& p, cudaStream_t stream, int bn = 0, int max_ctas = 0) {
   run_gemm(make_gemm_plan(op, p, bn, max_ctas), stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// attention
+// ---------------------------------------------------------------------------------------------------------
+// [B][N][ld] bf16 token-major tensor -> 3D map {ld cols, N, B} with box {64, 128, 1}
+inline CUtensorMap make_tmap_tokens_bf16(const void* base, uint64_t B, uint64_t N, uint64_t ld, uint64_t batch_stride) {
+  uint64_t dims[3] = {ld, N, B};
+  uint64_t str[2] = {ld * 2, batch_stride * 2};
+  uint32_t box[3] = {64, 128, 1};
+  return make_tmap_bf16(base, 3, dims, str, box);
+}
+
+struct AttnPlan {
+  CUtensorMap tmQ, tmK, tmV;
+  AttnParams p;
+  int grid = 0;
+};
+
+struct AttnOperands {
+  const __nv_bfloat16 *q, *k, *v;  // token-major [B][N][ld]
+  int ldq, ldk, ldv;
+  long long q_bs, k_bs, v_bs;      // batch strides in elements
+  int Nq_total;
+};
+
+inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
+  DCLIP_REQUIRE(p.B > 0 && p.H > 0 && p.Nk > 0 && p.Nq_total > p.q_start, "bad attention shape");
+  DCLIP_REQUIRE(p.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && p.out_batch_stride % 8 == 0, "attention out alignment");
+  AttnPlan plan;
+  plan.p = p;
+  plan.tmQ = make_tmap_tokens_bf16(op.q, p.B, op.Nq_total, op.ldq, op.q_bs);
+  plan.tmK = make_tmap_tokens_bf16(op.k, p.B, p.Nk, op.ldk, op.k_bs);
+  plan.tmV = make_tmap_tokens_bf16(op.v, p.B, p.Nk, op.ldv, op.v_bs);
+  const int nqb = (p.Nq_total - p.q_start + 255) / 256;
+  plan.grid = nqb * p.H * p.B;
+  return plan;
+}
+
+inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  attn_fwd_tcgen05_kernel<<<plan.grid, AttnCfg::THREADS, AttnCfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.p);
+  DCLIP_CHECK_CUDA(cudaGetLastError());
+}
+
+inline void run_attn_small(const SmallAttnParams& p, cudaStream_t stream) {
+  DCLIP_REQUIRE(p.q_count > 0 && p.Nk > 0, "bad small-attention shape");
+  const size_t smem = (size_t(p.Nk) + 64 + 512 + 16) * 4;
+  DCLIP_REQUIRE(smem <= 48 * 1024, "small attention: Nk=%d too large for the smem score buffer", p.Nk);
+  attn_small_kernel<<<p.B * p.H * p.q_count, 256, smem, stream>>>(p);
+  DCLIP_CHECK_CUDA(cudaGetLastError());
 }
 
 }  // namespace dclip

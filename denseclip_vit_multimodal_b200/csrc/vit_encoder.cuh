@@ -1,0 +1,346 @@
+// CLIPVisionTransformer.forward (segmentation/denseclip/models.py:543-597) as one native call.
+//
+// Data layout in HBM (token-major, B images flattened into M = B * Ntok rows; Ntok = 1 + gh*gw, CLS at row 0):
+//   x     fp32 [M, D]        residual stream, never rounded to bf16
+//   h     bf16 [M, D*s]      LayerNorm output / attention output (A operand of the next GEMM), s = 2 in precise mode (hi|lo)
+//   qkv   bf16 [M, 3D]       fused in_proj output, head-interleaved columns [q | k | v]   (precise: fp32 [M, 3D])
+//   g     bf16 [M, 4D*s]     QuickGELU(c_fc) output; the patch im2col matrix aliases it before layer 0
+//   pos   fp32 [Ntok, D]     positional embedding interpolated to (gh, gw)
+//   lnp   fp32 [M, D]        ln_post output (only when the last layer is tapped)
+// Per layer: LN -> QKV GEMM -> flash attention (+ CLS-query side kernel) -> out-proj GEMM (+bias +residual, in place on x)
+//            -> LN -> c_fc GEMM (+bias +QuickGELU) -> c_proj GEMM (+bias +residual, in place) -> optional taps.
+#pragma once
+#include <vector>
+
+#include "host_utils.cuh"
+#include "rowwise.cuh"
+
+namespace dclip {
+
+// fp32 CUDA-core flash attention for the precise ("fp32") path: one thread per query row, K/V tiles broadcast
+// from shared memory.  qkv fp32 [B][N][3D]; writes bf16 hi|lo split rows [M, 2D] for the split-bf16 out-proj GEMM.
+__global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int N,
+                                                      int D, float scale) {
+  __shared__ float4 Ks[32][16];
+  __shared__ float4 Vs[32][16];
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int qi = blockIdx.x * 128 + threadIdx.x;
+  const long long ld = 3LL * D;
+  const float* base = qkv + (long long)b * N * ld;
+  float q[64], o[64];
+  const bool active = qi < N;
+  {
+    const float4* qp = reinterpret_cast<const float4*>(base + (long long)(active ? qi : 0) * ld + h * 64);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+      const float4 t = qp[d];
+      q[4 * d] = t.x * scale; q[4 * d + 1] = t.y * scale; q[4 * d + 2] = t.z * scale; q[4 * d + 3] = t.w * scale;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 64; ++d) o[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < N; k0 += 32) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = threadIdx.x + 128 * i;  // 512 float4 per tile
+      const int j = idx >> 4, d4 = idx & 15;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (k0 + j < N) {
+        kv = *reinterpret_cast<const float4*>(base + (long long)(k0 + j) * ld + D + h * 64 + 4 * d4);
+        vv = *reinterpret_cast<const float4*>(base + (long long)(k0 + j) * ld + 2 * D + h * 64 + 4 * d4);
+      }
+      Ks[j][d4] = kv;
+      Vs[j][d4] = vv;
+    }
+    __syncthreads();
+    float s[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; d += 2) {
+        const float4 k0v = Ks[j][d], k1v = Ks[j][d + 1];
+        a0 += q[4 * d] * k0v.x + q[4 * d + 1] * k0v.y + q[4 * d + 2] * k0v.z + q[4 * d + 3] * k0v.w;
+        a1 += q[4 * d + 4] * k1v.x + q[4 * d + 5] * k1v.y + q[4 * d + 6] * k1v.z + q[4 * d + 7] * k1v.w;
+      }
+      s[j] = (k0 + j < N) ? a0 + a1 : -INFINITY;
+      mx = fmaxf(mx, s[j]);
+    }
+    const float m_new = fmaxf(m, mx);
+    const float alpha = expf(m - m_new);
+    l *= alpha;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) o[d] *= alpha;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float pj = expf(s[j] - m_new);
+      l += pj;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const float4 vv = Vs[j][d];
+        o[4 * d] += pj * vv.x; o[4 * d + 1] += pj * vv.y; o[4 * d + 2] += pj * vv.z; o[4 * d + 3] += pj * vv.w;
+      }
+    }
+    m = m_new;
+  }
+  if (!active) return;
+  const float inv = 1.f / l;
+  __nv_bfloat16* orow = out + ((long long)b * N + qi) * (2LL * D) + h * 64;
+#pragma unroll
+  for (int d = 0; d < 64; d += 2) {
+    const float a = o[d] * inv, c = o[d + 1] * inv;
+    const uint32_t hi = pack_bf16x2(a, c);
+    *reinterpret_cast<uint32_t*>(orow + d) = hi;
+    *reinterpret_cast<uint32_t*>(orow + D + d) = pack_bf16x2(a - __uint_as_float(hi << 16), c - __uint_as_float(hi & 0xffff0000u));
+  }
+}
+
+struct VitConfig {
+  int width = 768, layers = 12, heads = 12, patch = 16, grid0 = 14, precise = 0;
+};
+
+struct VitLayerWeights {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const __nv_bfloat16 *in_proj_w, *out_proj_w, *fc_w, *proj_w;
+  const float *in_proj_b, *out_proj_b, *fc_b, *proj_b;
+};
+
+struct VitWeights {
+  const __nv_bfloat16* conv1_w = nullptr;
+  const float *class_embedding = nullptr, *positional_embedding = nullptr;
+  const float *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr, *ln_post_b = nullptr;
+  std::vector<VitLayerWeights> layers;
+};
+
+struct VitTap {
+  int layer;
+  float* nchw;
+  __nv_bfloat16* tokens_bf16;
+};
+
+struct VitOutputs {
+  std::vector<VitTap> taps;
+  float* last_tokens_f32 = nullptr;
+};
+
+class VitEncoder {
+ public:
+  VitConfig cfg;
+  VitWeights weights;
+
+  void configure(const VitConfig& c) {
+    DCLIP_REQUIRE(c.width % 128 == 0 && c.width <= 1024, "ViT width %d must be a multiple of 128 and <= 1024", c.width);
+    DCLIP_REQUIRE(c.heads * 64 == c.width, "ViT head_dim must be 64 (width %d, heads %d)", c.width, c.heads);
+    DCLIP_REQUIRE(c.patch % 2 == 0 && c.layers > 0 && c.grid0 > 0, "bad ViT config");
+    cfg = c;
+    invalidate_plans();
+  }
+  void invalidate_plans() { plan_key_ = PlanKey{}; }
+
+  int kp() const { return (3 * cfg.patch * cfg.patch + 7) & ~7; }  // im2col row pitch (elements, per hi/lo half)
+
+  struct Layout {
+    size_t x, h, qkv, g, pos, lnp, total;
+    int gh, gw, P, Ntok, M;
+  };
+
+  Layout layout(int B, int H, int W) const {
+    Layout L{};
+    L.gh = H / cfg.patch; L.gw = W / cfg.patch; L.P = L.gh * L.gw; L.Ntok = L.P + 1; L.M = B * L.Ntok;
+    const size_t D = cfg.width, s = cfg.precise ? 2 : 1, M = L.M;
+    auto up = [](size_t v) { return (v + 1023) & ~size_t(1023); };
+    size_t off = 0;
+    L.x = off; off += up(M * D * 4);
+    L.h = off; off += up(M * D * s * 2);
+    L.qkv = off; off += up(M * 3 * D * (cfg.precise ? 4 : 2));
+    const size_t g_bytes = M * 4 * D * s * 2, patch_bytes = size_t(B) * L.P * kp() * s * 2;
+    L.g = off; off += up(g_bytes > patch_bytes ? g_bytes : patch_bytes);
+    L.pos = off; off += up(size_t(L.Ntok) * D * 4);
+    L.lnp = off; off += up(M * D * 4);
+    L.total = off;
+    return L;
+  }
+
+  size_t workspace_bytes(int B, int H, int W) const {
+    DCLIP_REQUIRE(B > 0 && H >= cfg.patch && W >= cfg.patch, "bad image shape %dx%dx%d", B, H, W);
+    return layout(B, H, W).total;
+  }
+
+  // returns the number of kernel launches
+  int forward(const float* img, int B, int H, int W, void* ws, size_t ws_bytes, const VitOutputs& outs, cudaStream_t st) {
+    DCLIP_REQUIRE(int(weights.layers.size()) == cfg.layers && weights.conv1_w, "ViT weights not set");
+    const Layout L = layout(B, H, W);
+    DCLIP_REQUIRE(ws_bytes >= L.total, "workspace too small: %zu < %zu", ws_bytes, L.total);
+    DCLIP_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024B aligned");
+    for (const VitTap& t : outs.taps) DCLIP_REQUIRE(t.layer >= 0 && t.layer < cfg.layers, "tap layer %d out of range", t.layer);
+    build_plans(B, H, W, ws, L);
+    int n = 0;
+    const int D = cfg.width, s = cfg.precise ? 2 : 1;
+    uint8_t* w8 = static_cast<uint8_t*>(ws);
+    float* x = reinterpret_cast<float*>(w8 + L.x);
+    __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(w8 + L.h);
+    float* pos = reinterpret_cast<float*>(w8 + L.pos);
+    float* lnp = reinterpret_cast<float*>(w8 + L.lnp);
+    __nv_bfloat16* patches = reinterpret_cast<__nv_bfloat16*>(w8 + L.g);
+
+    // ---- patch embed + CLS + positional embedding (models.py:546-556) ----
+    if (L.P == cfg.grid0 * cfg.grid0) {
+      DCLIP_CHECK_CUDA(cudaMemcpyAsync(pos, weights.positional_embedding, size_t(L.Ntok) * D * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      posemb_interp_kernel<<<L.Ntok, 256, 0, st>>>(weights.positional_embedding, pos, cfg.grid0, L.gh, L.gw, D);
+      ++n;
+    }
+    Im2colParams ic{img, patches, (long long)kp() * s, B, H, W, cfg.patch, L.gh, L.gw, cfg.precise, kp()};
+    if (kp() != 3 * cfg.patch * cfg.patch) DCLIP_CHECK_CUDA(cudaMemsetAsync(patches, 0, size_t(B) * L.P * kp() * s * 2, st));
+    launch_im2col(ic, st); ++n;
+    run_gemm(patch_plan_, st); ++n;
+    cls_row_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(x, weights.class_embedding, pos, B, L.Ntok, D); ++n;
+    // ---- ln_pre (in place on the residual stream) ----
+    LayerNormParams lp{x, D, weights.ln_pre_g, weights.ln_pre_b, 1e-5f, L.M, D, x, D, nullptr, 0, 0, 0};
+    launch_layernorm(lp, st); ++n;
+
+    size_t tap_i = 0;
+    for (int li = 0; li < cfg.layers; ++li) {
+      const VitLayerWeights& lw = weights.layers[li];
+      LayerNormParams l1{x, D, lw.ln1_g, lw.ln1_b, 1e-5f, L.M, D, nullptr, 0, hbuf, (long long)D * s, cfg.precise, D};
+      launch_layernorm(l1, st); ++n;
+      run_gemm(layer_plans_[li].qkv, st); ++n;
+      if (cfg.precise) {
+        dim3 grid((L.Ntok + 127) / 128, cfg.heads, B);
+        attn_f32_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(w8 + L.qkv), hbuf, L.Ntok, D, 0.125f); ++n;
+      } else {
+        run_attn(attn_plan_, st); ++n;
+        if (attn_plan_.p.q_start == 1) { run_attn_small(cls_attn_, st); ++n; }
+      }
+      run_gemm(layer_plans_[li].out_proj, st); ++n;
+      LayerNormParams l2{x, D, lw.ln2_g, lw.ln2_b, 1e-5f, L.M, D, nullptr, 0, hbuf, (long long)D * s, cfg.precise, D};
+      launch_layernorm(l2, st); ++n;
+      run_gemm(layer_plans_[li].fc, st); ++n;
+      run_gemm(layer_plans_[li].proj, st); ++n;
+
+      // ---- feature taps (models.py:568-582) ----
+      while (tap_i < outs.taps.size() && outs.taps[tap_i].layer < li) ++tap_i;
+      const bool last = li == cfg.layers - 1;
+      bool lnp_done = false;
+      auto ensure_lnp = [&] {
+        if (lnp_done) return;
+        LayerNormParams lq{x, D, weights.ln_post_g, weights.ln_post_b, 1e-5f, L.M, D, lnp, D, nullptr, 0, 0, 0};
+        launch_layernorm(lq, st); ++n;
+        lnp_done = true;
+      };
+      for (size_t t = tap_i; t < outs.taps.size() && outs.taps[t].layer == li; ++t) {
+        const VitTap& tp = outs.taps[t];
+        const float* src = x;
+        if (last) { ensure_lnp(); src = lnp; }
+        if (tp.nchw) { launch_tap_nchw(src, tp.nchw, B, L.Ntok, D, st); ++n; }
+        if (tp.tokens_bf16) {
+          CastParams cp{src, D, tp.tokens_bf16, D, L.M, D, 0, 0, 1.0f};
+          cast_bf16_kernel<<<148 * 8, 256, 0, st>>>(cp); ++n;
+        }
+      }
+      if (last && outs.last_tokens_f32) {
+        ensure_lnp();
+        DCLIP_CHECK_CUDA(cudaMemcpyAsync(outs.last_tokens_f32, lnp, size_t(L.M) * D * 4, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    DCLIP_CHECK_CUDA(cudaGetLastError());
+    return n;
+  }
+
+ private:
+  struct PlanKey {
+    int B = 0, H = 0, W = 0;
+    void* ws = nullptr;
+    bool operator==(const PlanKey& o) const { return B == o.B && H == o.H && W == o.W && ws == o.ws; }
+  };
+  struct LayerPlans {
+    GemmPlan qkv, out_proj, fc, proj;
+  };
+  PlanKey plan_key_;
+  GemmPlan patch_plan_;
+  std::vector<LayerPlans> layer_plans_;
+  AttnPlan attn_plan_;
+  SmallAttnParams cls_attn_;
+
+  void build_plans(int B, int H, int W, void* ws, const Layout& L) {
+    const PlanKey key{B, H, W, ws};
+    if (key == plan_key_ && int(layer_plans_.size()) == cfg.layers) return;
+    const int D = cfg.width, s = cfg.precise ? 2 : 1, M = L.M;
+    uint8_t* w8 = static_cast<uint8_t*>(ws);
+    float* x = reinterpret_cast<float*>(w8 + L.x);
+    __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(w8 + L.h);
+    __nv_bfloat16* gbuf = reinterpret_cast<__nv_bfloat16*>(w8 + L.g);
+    float* pos = reinterpret_cast<float*>(w8 + L.pos);
+    const int K0 = kp();
+    {
+      // patch-embed GEMM: rows m = b*P + p -> token row b*Ntok + 1 + p, + pos[1 + p]
+      GemmOperands op{gbuf, K0 * s, weights.conv1_w, K0 * s};
+      GemmParams p{};
+      p.M = B * L.P; p.N = D; p.K = K0; p.split_in = cfg.precise; p.out_scale = 1.f;
+      p.residual = pos; p.ldr = D; p.res_mod = 1; p.remap_P = L.P; p.remap_Nt = L.Ntok;
+      p.out_f32 = x; p.ldc = D;
+      patch_plan_ = make_gemm_plan(op, p);
+    }
+    layer_plans_.assign(cfg.layers, LayerPlans{});
+    for (int li = 0; li < cfg.layers; ++li) {
+      const VitLayerWeights& lw = weights.layers[li];
+      LayerPlans& lp = layer_plans_[li];
+      {
+        GemmOperands op{hbuf, D * s, lw.in_proj_w, D * s};
+        GemmParams p{};
+        p.M = M; p.N = 3 * D; p.K = D; p.split_in = cfg.precise; p.bias = lw.in_proj_b; p.out_scale = 1.f;
+        if (cfg.precise) { p.out_f32 = reinterpret_cast<float*>(w8 + L.qkv); p.ldc = 3 * D; }
+        else { p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(w8 + L.qkv); p.ldcb = 3 * D; }
+        lp.qkv = make_gemm_plan(op, p);
+      }
+      {
+        GemmOperands op{hbuf, D * s, lw.out_proj_w, D * s};
+        GemmParams p{};
+        p.M = M; p.N = D; p.K = D; p.split_in = cfg.precise; p.bias = lw.out_proj_b; p.out_scale = 1.f;
+        p.residual = x; p.ldr = D; p.out_f32 = x; p.ldc = D;
+        lp.out_proj = make_gemm_plan(op, p);
+      }
+      {
+        GemmOperands op{hbuf, D * s, lw.fc_w, D * s};
+        GemmParams p{};
+        p.M = M; p.N = 4 * D; p.K = D; p.split_in = cfg.precise; p.bias = lw.fc_b; p.out_scale = 1.f;
+        p.act = cfg.precise ? ACT_QUICKGELU_PRECISE : ACT_QUICKGELU;
+        p.out_bf16 = gbuf; p.ldcb = 4 * D * s; p.split_out = cfg.precise; p.split_out_off = 4 * D;
+        lp.fc = make_gemm_plan(op, p);
+      }
+      {
+        GemmOperands op{gbuf, 4 * D * s, lw.proj_w, 4 * D * s};
+        GemmParams p{};
+        p.M = M; p.N = D; p.K = 4 * D; p.split_in = cfg.precise; p.bias = lw.proj_b; p.out_scale = 1.f;
+        p.residual = x; p.ldr = D; p.out_f32 = x; p.ldc = D;
+        lp.proj = make_gemm_plan(op, p);
+      }
+    }
+    if (!cfg.precise) {
+      const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(w8 + L.qkv);
+      const long long bs = (long long)L.Ntok * 3 * D;
+      AttnOperands op{qkv, qkv, qkv, 3 * D, 3 * D, 3 * D, bs, bs, bs, L.Ntok};
+      AttnParams p{};
+      p.B = B; p.H = cfg.heads; p.Nq_total = L.Ntok; p.Nk = L.Ntok;
+      // N = 1 + 256k (512x1024 and 512x512 at ps 16): start the tensor-core kernel at row 1 and give the CLS query to
+      // the side kernel, so every CTA owns a full 256-row block
+      p.q_start = (L.Ntok > 1 && (L.Ntok - 1) % 256 == 0) ? 1 : 0;
+      p.q_col0 = 0; p.k_col0 = D; p.v_col0 = 2 * D;
+      p.scale_log2 = 0.125f * 1.4426950408889634f;
+      p.out = hbuf; p.out_batch_stride = (long long)L.Ntok * D; p.ldo = D;
+      attn_plan_ = make_attn_plan(op, p);
+      SmallAttnParams sp{};
+      sp.q = sp.k = sp.v = qkv; sp.is_f32 = 0; sp.B = B; sp.H = cfg.heads; sp.Nk = L.Ntok; sp.q_first = 0; sp.q_count = 1;
+      sp.ldq = sp.ldk = sp.ldv = 3 * D; sp.q_bs = sp.k_bs = sp.v_bs = bs;
+      sp.q_col0 = 0; sp.k_col0 = D; sp.v_col0 = 2 * D; sp.scale = 0.125f; sp.causal = 0;
+      sp.out = hbuf; sp.out_f32 = 0; sp.ldo = D; sp.out_bs = (long long)L.Ntok * D; sp.out_split_off = 0;
+      cls_attn_ = sp;
+    }
+    plan_key_ = key;
+  }
+};
+
+}  // namespace dclip
