@@ -264,6 +264,18 @@ int dclip_upsample_bilinear(dclip_handle_t h, const float* in, int in_nchw, long
   });
 }
 
+int dclip_upsample_argmax(dclip_handle_t h, const float* in, long long ldi, long long in_bs, int B, int K, int hh, int ww,
+                          int H, int W, uint8_t* out, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(W % 4 == 0 && K > 0 && K <= 256, "upsample_argmax: W %% 4 == 0 and K <= 256 required");
+    UpsampleArgmaxParams p{in, ldi, in_bs, out, B, K, hh, ww, H, W};
+    const long long total = (long long)B * H * (W / 4);
+    const int grid = int(std::min<long long>((total + 255) / 256, 148 * 32));
+    upsample_argmax_kernel<<<std::max(grid, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    check_launch(h);
+  });
+}
+
 int dclip_gamma_residual(dclip_handle_t h, const float* a, const float* gamma, const float* d, float* out, long long n,
                          int C, void* stream) {
   return guarded(h, [&] {

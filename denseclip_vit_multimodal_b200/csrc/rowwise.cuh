@@ -371,6 +371,50 @@ __global__ void __launch_bounds__(256) conv3x3_gather_kernel(const Conv3x3Gather
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused bilinear upsample + channel argmax (simple_test's `seg_logit.argmax(dim=1)`, denseclip.py:987-1000) without
+// materialising the [B, K, H, W] logits: in = token-major fp32 [B, h*w, ldi] low-res logits, out = uint8 [B, H, W].
+// Ties resolve to the lowest class index, like torch.argmax.  One thread per 4 output pixels along W.
+// ---------------------------------------------------------------------------------------------------------
+struct UpsampleArgmaxParams {
+  const float* in; long long ldi; long long in_bs;
+  uint8_t* out;
+  int B, K, h, w, H, W;
+};
+
+__global__ void __launch_bounds__(256) upsample_argmax_kernel(const UpsampleArgmaxParams p) {
+  const int W4 = p.W >> 2;
+  const long long total = (long long)p.B * p.H * W4;
+  const float sy = float(p.h) / float(p.H), sx = float(p.w) / float(p.W);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x4 = int(i % W4);
+    const int y = int((i / W4) % p.H);
+    const int b = int(i / ((long long)W4 * p.H));
+    int y0, y1;
+    float ly0, ly1;
+    bilinear_src(y, sy, p.h, y0, y1, ly0, ly1);
+    uint32_t packed = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int x0, x1;
+      float lx0, lx1;
+      bilinear_src(x4 * 4 + e, sx, p.w, x0, x1, lx0, lx1);
+      const float* r00 = p.in + (long long)b * p.in_bs + (long long)(y0 * p.w + x0) * p.ldi;
+      const float* r01 = p.in + (long long)b * p.in_bs + (long long)(y0 * p.w + x1) * p.ldi;
+      const float* r10 = p.in + (long long)b * p.in_bs + (long long)(y1 * p.w + x0) * p.ldi;
+      const float* r11 = p.in + (long long)b * p.in_bs + (long long)(y1 * p.w + x1) * p.ldi;
+      float best = -INFINITY;
+      int arg = 0;
+      for (int k = 0; k < p.K; ++k) {
+        const float v = ly0 * (lx0 * r00[k] + lx1 * r01[k]) + ly1 * (lx0 * r10[k] + lx1 * r11[k]);
+        if (v > best) { best = v; arg = k; }
+      }
+      packed |= uint32_t(arg) << (8 * e);
+    }
+    *reinterpret_cast<uint32_t*>(p.out + ((long long)b * p.H + y) * p.W + x4 * 4) = packed;
+  }
+}
+
 // out[i] = a[i] + gamma[i % C] * d[i]     (text + gamma * text_diff, denseclip.py:665)
 __global__ void gamma_residual_kernel(const float* __restrict__ a, const float* __restrict__ g, const float* __restrict__ d,
                                       float* __restrict__ out, long long n, int C) {

@@ -300,7 +300,7 @@ class DenseCLIP(nn.Module):
         return text, feats, score, x_orig
 
     # ---- forward ----
-    def _heads_native(self, feat_b: torch.Tensor, gh: int, gw: int, out_hw):
+    def _heads_native(self, feat_b: torch.Tensor, gh: int, gw: int, out_hw, class_map: bool = False):
         B = feat_b.shape[0]
         seg = depth = None
         if self.with_decode_head:
@@ -312,7 +312,17 @@ class DenseCLIP(nn.Module):
             y, n = self.depth_head.forward_tokens(feat_b, gh, gw)
             depth = (y.view(B, gh * gw, -1), n)
         up = lambda t: None if t is None else ops.upsample_bilinear(t[0], out_hw, tokens_hw=(gh, gw), channels=t[1])  # noqa: E731
+        if class_map:
+            seg_map = None if seg is None else ops.upsample_argmax(seg[0], out_hw, tokens_hw=(gh, gw), channels=seg[1])
+            return seg_map, up(depth)
         return up(seg), up(depth)
+
+    @torch.no_grad()
+    def predict(self, img):
+        """Batched on-device counterpart of ``simple_test`` (denseclip.py:987-1000): {'seg': uint8 class map [B,H,W],
+        'depth': fp32 [B,1,H,W]}.  The argmax is fused with the bilinear upsample, so full-resolution logits are never
+        written."""
+        return self.forward(img, return_loss=False, _class_map=True)
 
     def forward(self, img, img_metas=None, gt_semantic_seg=None, return_loss=True, **kwargs):
         """Reference denseclip.py:702-916.  Inference returns {'seg': [B,K,H,W], 'depth': [B,1,H,W]} fp32; the training
@@ -354,7 +364,7 @@ class DenseCLIP(nn.Module):
             out_hw = tuple(gt.shape[-2:]) if gt is not None else (gh, gw)
             seg, depth = self._heads_native(feat_b, gh, gw, out_hw)
             return {'main_output': seg, 'depth_output': depth, 'aux_losses': {}}
-        seg, depth = self._heads_native(feat_b, gh, gw, tuple(img.shape[2:]))
+        seg, depth = self._heads_native(feat_b, gh, gw, tuple(img.shape[2:]), class_map=bool(kwargs.get('_class_map', False)))
         return {'seg': seg, 'depth': depth}
 
     # ---- inference helpers (reference denseclip.py:938-1041) ----

@@ -214,6 +214,17 @@ def upsample_bilinear(x: torch.Tensor, size, *, tokens_hw=None, channels=None) -
     return out
 
 
+def upsample_argmax(x: torch.Tensor, size, *, tokens_hw, channels) -> torch.Tensor:
+    """token-major fp32 low-res logits [B, h*w, ld] -> uint8 class map [B, H, W] (bilinear upsample + argmax, fused)."""
+    x = _req(x, torch.float32, "x")
+    H, W = size
+    hh, ww = tokens_hw
+    out = torch.empty(x.shape[0], H, W, dtype=torch.uint8, device=x.device)
+    _call(x, _lib.lib().dclip_upsample_argmax, _ptr(x), x.stride(1), x.stride(0), x.shape[0], channels, hh, ww, H, W, _ptr(out),
+          _stream(x))
+    return out
+
+
 def gamma_residual(a: torch.Tensor, gamma: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
     a = _req(a.contiguous(), torch.float32, "a")
     d = _req(d.contiguous(), torch.float32, "d")

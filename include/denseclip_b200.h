@@ -111,6 +111,10 @@ int dclip_score_map(dclip_handle_t h, const float* vis, long long ld, long long 
                     int K, int C, int P, float eps, float* score, void* stream);
 int dclip_upsample_bilinear(dclip_handle_t h, const float* in, int in_nchw, long long ldi, long long in_bs, int B, int C,
                             int hh, int ww, int H, int W, float* out, void* stream);
+/* fused bilinear upsample + argmax over K channels: in token-major fp32 [B, hh*ww, ldi] -> uint8 class map [B, H, W]
+ * (simple_test's seg_logit.argmax(dim=1), denseclip.py:987-1000, without materialising the logits) */
+int dclip_upsample_argmax(dclip_handle_t h, const float* in, long long ldi, long long in_bs, int B, int K, int hh, int ww,
+                          int H, int W, uint8_t* out, void* stream);
 int dclip_gamma_residual(dclip_handle_t h, const float* a, const float* gamma, const float* d, float* out, long long n,
                          int C, void* stream);
 /* 3x3 / pad 1 / stride 1 conv operand gather: in token-major [B][row0 + y*w + x][ld] (fp32 or bf16, C channels) ->
