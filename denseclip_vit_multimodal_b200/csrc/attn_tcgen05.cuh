@@ -367,31 +367,41 @@ __device__ __forceinline__ float ld_elem(const void* base, int is_f32, long long
   return is_f32 ? reinterpret_cast<const float*>(base)[idx] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
 }
 
-// dynamic smem: Nk floats (scores) + 64 (q) + 8*64 (partial O) + 16 (reduction scratch)
+// dynamic smem: QB*Nk floats (scores) + QB*64 (q) + 8*QB*64 (partial O) + 16*QB (reduction scratch).
+// QB = queries handled per CTA (they share every K/V load); a CTA covers queries [q0, q0 + QB) of one (batch, head).
+template <int QB>
 __global__ void __launch_bounds__(256) attn_small_kernel(const SmallAttnParams p) {
   extern __shared__ float sm[];
-  float* sc = sm;
-  float* sq = sm + p.Nk;
-  float* so = sq + 64;
-  float* red = so + 512;
+  float* sc = sm;                       // [QB][Nk]
+  float* sq = sm + QB * p.Nk;           // [QB][64]
+  float* so = sq + QB * 64;             // [8 warps][QB][64]
+  float* red = so + 8 * QB * 64;        // [2][8][QB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int qi = p.q_first + blockIdx.x % p.q_count;
-  const int h = (blockIdx.x / p.q_count) % p.H;
-  const int b = blockIdx.x / (p.q_count * p.H);
-  const int nk = p.causal ? min(p.Nk, qi + 1) : p.Nk;
-  if (tid < 64) sq[tid] = ld_elem(p.q, p.is_f32, b * p.q_bs + (long long)qi * p.ldq + p.q_col0 + h * 64 + tid) * p.scale;
+  const int nqb = (p.q_count + QB - 1) / QB;
+  const int q0 = p.q_first + (blockIdx.x % nqb) * QB;
+  const int h = (blockIdx.x / nqb) % p.H;
+  const int b = blockIdx.x / (nqb * p.H);
+  const int nq = min(QB, p.q_first + p.q_count - q0);
+  // causal: query qi may see keys j <= qi; the CTA scans up to its last query's limit and masks per query
+  const int nk = p.causal ? min(p.Nk, q0 + nq) : p.Nk;
+  for (int i = tid; i < QB * 64; i += 256) {
+    const int qq = i >> 6, d = i & 63;
+    sq[i] = qq < nq ? ld_elem(p.q, p.is_f32, b * p.q_bs + (long long)(q0 + qq) * p.ldq + p.q_col0 + h * 64 + d) * p.scale : 0.f;
+  }
   __syncthreads();
-  // phase 1: scores
-  float mx = -INFINITY;
+  // phase 1: scores, one key per thread per iteration, all QB queries against the same K row
+  float mx[QB];
+#pragma unroll
+  for (int qq = 0; qq < QB; ++qq) mx[qq] = -INFINITY;
   for (int j = tid; j < nk; j += 256) {
     const long long koff = b * p.k_bs + (long long)j * p.ldk + p.k_col0 + h * 64;
-    float s = 0.f;
+    float kf[64];
     if (p.is_f32) {
       const float4* kp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.k) + koff);
 #pragma unroll
       for (int d = 0; d < 16; ++d) {
         const float4 kv = kp[d];
-        s += sq[4 * d] * kv.x + sq[4 * d + 1] * kv.y + sq[4 * d + 2] * kv.z + sq[4 * d + 3] * kv.w;
+        kf[4 * d] = kv.x; kf[4 * d + 1] = kv.y; kf[4 * d + 2] = kv.z; kf[4 * d + 3] = kv.w;
       }
     } else {
       const uint4* kp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.k) + koff);
@@ -400,89 +410,123 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const SmallAttnParams p
         const uint4 kv = kp[d];
         const uint32_t w[4] = {kv.x, kv.y, kv.z, kv.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          s += sq[8 * d + 2 * e] * __uint_as_float(w[e] << 16) + sq[8 * d + 2 * e + 1] * __uint_as_float(w[e] & 0xffff0000u);
+        for (int e = 0; e < 4; ++e) {
+          kf[8 * d + 2 * e] = __uint_as_float(w[e] << 16);
+          kf[8 * d + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+        }
       }
     }
-    sc[j] = s;
-    mx = fmaxf(mx, s);
+#pragma unroll
+    for (int qq = 0; qq < QB; ++qq) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 64; d += 2) {
+        s0 += sq[qq * 64 + d] * kf[d];
+        s1 += sq[qq * 64 + d + 1] * kf[d + 1];
+      }
+      float s = s0 + s1;
+      if (p.causal && j > q0 + qq) s = -INFINITY;
+      sc[qq * p.Nk + j] = s;
+      mx[qq] = fmaxf(mx[qq], s);
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  mx = red[0];
+  for (int qq = 0; qq < QB; ++qq) {
 #pragma unroll
-  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
-  float sum = 0.f;
+    for (int o = 16; o > 0; o >>= 1) mx[qq] = fmaxf(mx[qq], __shfl_xor_sync(0xffffffffu, mx[qq], o));
+    if (lane == 0) red[warp * QB + qq] = mx[qq];
+  }
+  __syncthreads();
+  float sum[QB];
+#pragma unroll
+  for (int qq = 0; qq < QB; ++qq) {
+    float m = red[qq];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w * QB + qq]);
+    mx[qq] = m;
+    sum[qq] = 0.f;
+  }
   for (int j = tid; j < nk; j += 256) {
-    const float e = __expf(sc[j] - mx);
-    sc[j] = e;
-    sum += e;
+#pragma unroll
+    for (int qq = 0; qq < QB; ++qq) {
+      const float e = __expf(sc[qq * p.Nk + j] - mx[qq]);
+      sc[qq * p.Nk + j] = e;
+      sum[qq] += e;
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if (lane == 0) red[8 + warp] = sum;
+  for (int qq = 0; qq < QB; ++qq) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum[qq] += __shfl_xor_sync(0xffffffffu, sum[qq], o);
+    if (lane == 0) red[8 * QB + warp * QB + qq] = sum[qq];
+  }
   __syncthreads();
-  sum = 0.f;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) sum += red[8 + w];
-  // phase 2: O[d] = sum_j p_j V[j][d]; thread (g, d8) covers keys j = g, g+32, ... and 8 consecutive dims
-  // (one 16 B / 32 B vector load per key; 4 keys in flight per thread)
+  // phase 2: O[q][d] = sum_j p[q][j] V[j][d]; thread (g, d8) covers keys j = g, g+32, ... and 8 consecutive dims
   const int d8 = tid & 7, g = tid >> 3;
-  float acc[8];
+  float acc[QB][8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[qq][e] = 0.f;
   const long long vbase = b * p.v_bs + p.v_col0 + h * 64 + d8 * 8;
-  for (int j0 = g; j0 < nk; j0 += 128) {
-    float pj[4];
-    uint4 raw[4][2];
+  for (int j0 = g; j0 < nk; j0 += 64) {
+    float vf[2][8];
+    int jj[2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 2; ++u) {
       const int j = j0 + 32 * u;
-      pj[u] = j < nk ? sc[j] : 0.f;
+      jj[u] = j;
       const long long voff = vbase + (long long)(j < nk ? j : j0) * p.ldv;
       if (p.is_f32) {
-        const uint4* vp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.v) + voff);
-        raw[u][0] = vp[0];
-        raw[u][1] = vp[1];
+        const float4* vp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.v) + voff);
+        const float4 a = vp[0], c = vp[1];
+        vf[u][0] = a.x; vf[u][1] = a.y; vf[u][2] = a.z; vf[u][3] = a.w; vf[u][4] = c.x; vf[u][5] = c.y; vf[u][6] = c.z; vf[u][7] = c.w;
       } else {
-        raw[u][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.v) + voff);
+        const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.v) + voff);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          vf[u][2 * e] = __uint_as_float(w[e] << 16);
+          vf[u][2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+        }
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (p.is_f32) {
-        const uint32_t w[8] = {raw[u][0].x, raw[u][0].y, raw[u][0].z, raw[u][0].w, raw[u][1].x, raw[u][1].y, raw[u][1].z, raw[u][1].w};
+    for (int u = 0; u < 2; ++u) {
+      if (jj[u] < nk) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += pj[u] * __uint_as_float(w[e]);
-      } else {
-        const uint32_t w[4] = {raw[u][0].x, raw[u][0].y, raw[u][0].z, raw[u][0].w};
+        for (int qq = 0; qq < QB; ++qq) {
+          const float pj = sc[qq * p.Nk + jj[u]];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          acc[2 * e] += pj[u] * __uint_as_float(w[e] << 16);
-          acc[2 * e + 1] += pj[u] * __uint_as_float(w[e] & 0xffff0000u);
+          for (int e = 0; e < 8; ++e) acc[qq][e] += pj * vf[u][e];
         }
       }
     }
   }
-  // reduce the 32 key groups: shuffle across the 4 groups inside a warp, then smem across the 8 warps
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
-  }
+  for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[qq][e] += __shfl_xor_sync(0xffffffffu, acc[qq][e], 8);
+      acc[qq][e] += __shfl_xor_sync(0xffffffffu, acc[qq][e], 16);
+    }
   if (lane < 8) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) so[warp * 64 + lane * 8 + e] = acc[e];
+    for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) so[(warp * QB + qq) * 64 + lane * 8 + e] = acc[qq][e];
   }
   __syncthreads();
-  if (tid < 64) {
-    float o = 0.f;
+  for (int i = tid; i < nq * 64; i += 256) {
+    const int qq = i >> 6, d = i & 63;
+    float o = 0.f, ssum = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) o += so[w * 64 + tid];
-    o /= sum;
-    const long long ooff = b * p.out_bs + (long long)qi * p.ldo + h * 64 + tid;
+    for (int w = 0; w < 8; ++w) {
+      o += so[(w * QB + qq) * 64 + d];
+      ssum += red[8 * QB + w * QB + qq];
+    }
+    o /= ssum;
+    const long long ooff = b * p.out_bs + (long long)(q0 + qq) * p.ldo + h * 64 + d;
     if (p.out_f32) {
       reinterpret_cast<float*>(p.out)[ooff] = o;
     } else {

@@ -240,14 +240,20 @@ int dclip_score_map(dclip_handle_t h, const float* vis, long long ld, long long 
     DCLIP_REQUIRE(C % 32 == 0 && C <= 1024, "score map: C=%d must be a multiple of 32 and <= 1024", C);
     const size_t smem = size_t(K) * C * 4;
     DCLIP_REQUIRE(smem <= 200 * 1024, "score map: K*C too large for shared memory");
-    static bool attr = false;
-    if (!attr) {
-      DCLIP_CHECK_CUDA(cudaFuncSetAttribute(score_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
-    }
     ScoreParams p{vis, ld, bs, row0, text, score, B, K, C, P, eps};
-    dim3 grid(std::min((P + 7) / 8, 64), B);
-    score_map_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    dim3 grid(std::min((P + 7) / 8, 128), B);
+    auto launch = [&](auto kern) {
+      DCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      kern<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    };
+    switch (C / 32) {
+      case 4: launch(score_map_kernel<4>); break;
+      case 8: launch(score_map_kernel<8>); break;
+      case 16: launch(score_map_kernel<16>); break;
+      case 24: launch(score_map_kernel<24>); break;
+      case 32: launch(score_map_kernel<32>); break;
+      default: throw Error{"score map: C must be one of 128, 256, 512, 768, 1024"};
+    }
     check_launch(h);
   });
 }
@@ -257,9 +263,16 @@ int dclip_upsample_bilinear(dclip_handle_t h, const float* in, int in_nchw, long
   return guarded(h, [&] {
     DCLIP_REQUIRE(W % 4 == 0, "upsample: output width must be a multiple of 4");
     UpsampleParams p{in, in_nchw, ldi, in_bs, out, B, C, hh, ww, H, W};
-    const long long total = (long long)B * C * H * (W / 4);
-    const int grid = int(std::min<long long>((total + 255) / 256, 148 * 32));
-    upsample_bilinear_kernel<<<std::max(grid, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    // token-major input whose rows hold (C rounded up to 4) readable floats: all-channel fast path
+    if (!in_nchw && ldi % 4 == 0 && ldi >= ((C + 3) & ~3) && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && in_bs % 4 == 0) {
+      const long long total = (long long)B * H * (W / 4);
+      const int grid = int(std::min<long long>((total + 255) / 256, 148 * 64));
+      upsample_bilinear_tok_kernel<<<std::max(grid, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    } else {
+      const long long total = (long long)B * C * H * (W / 4);
+      const int grid = int(std::min<long long>((total + 255) / 256, 148 * 32));
+      upsample_bilinear_kernel<<<std::max(grid, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    }
     check_launch(h);
   });
 }

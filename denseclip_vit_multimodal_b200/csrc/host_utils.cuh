@@ -143,6 +143,9 @@ inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
   if (p.act == ACT_QUICKGELU && flags == EPI_OUT_BF16) return launch_gemm_inst<BN, ACT_QUICKGELU, EPI_OUT_BF16>(plan, stream);
   if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32))
     return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32>(plan, stream);
+  if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32 | EPI_OUT_BF16))
+    return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32 | EPI_OUT_BF16>(plan, stream);
+  if (p.act == ACT_RELU && flags == EPI_OUT_BF16) return launch_gemm_inst<BN, ACT_RELU, EPI_OUT_BF16>(plan, stream);
   return launch_gemm_inst<BN, -1, -1>(plan, stream);
 }
 
@@ -241,12 +244,25 @@ inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
   DCLIP_CHECK_CUDA(cudaGetLastError());
 }
 
+template <int QB>
+inline void launch_attn_small(const SmallAttnParams& p, cudaStream_t stream) {
+  const size_t smem = (size_t(QB) * p.Nk + QB * 64 + 8 * QB * 64 + 16 * QB) * 4;
+  DCLIP_REQUIRE(smem <= 200 * 1024, "small attention: Nk=%d too large for the smem score buffer", p.Nk);
+  static bool attr = false;
+  if (!attr) {
+    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  const int nqb = (p.q_count + QB - 1) / QB;
+  attn_small_kernel<QB><<<p.B * p.H * nqb, 256, smem, stream>>>(p);
+  DCLIP_CHECK_CUDA(cudaGetLastError());
+}
+
 inline void run_attn_small(const SmallAttnParams& p, cudaStream_t stream) {
   DCLIP_REQUIRE(p.q_count > 0 && p.Nk > 0, "bad small-attention shape");
-  const size_t smem = (size_t(p.Nk) + 64 + 512 + 16) * 4;
-  DCLIP_REQUIRE(smem <= 48 * 1024, "small attention: Nk=%d too large for the smem score buffer", p.Nk);
-  attn_small_kernel<<<p.B * p.H * p.q_count, 256, smem, stream>>>(p);
-  DCLIP_CHECK_CUDA(cudaGetLastError());
+  if (p.q_count == 1) launch_attn_small<1>(p, stream);
+  else if (p.q_count <= 4 || p.Nk > 4096) launch_attn_small<4>(p, stream);
+  else launch_attn_small<8>(p, stream);
 }
 
 }  // namespace dclip

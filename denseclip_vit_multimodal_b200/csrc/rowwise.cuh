@@ -265,6 +265,7 @@ struct ScoreParams {
   float eps;
 };
 
+template <int NC>  // NC = C / 32 channels per lane
 __global__ void __launch_bounds__(256) score_map_kernel(const ScoreParams p) {
   extern __shared__ float st[];  // [K][C] normalised text of this image
   const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -278,17 +279,18 @@ __global__ void __launch_bounds__(256) score_map_kernel(const ScoreParams p) {
   __syncthreads();
   for (int px = blockIdx.x * 8 + w; px < p.P; px += gridDim.x * 8) {
     const float* v = p.vis + (long long)b * p.bs + (long long)(p.row0 + px) * p.ld;
-    float vv[32];  // C <= 1024
+    float vv[NC];
     float ss = 0.f;
-    const int nc = p.C / 32;
-    for (int i = 0; i < nc; ++i) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
       vv[i] = v[lane + 32 * i];
       ss += vv[i] * vv[i];
     }
     const float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), p.eps);
     for (int k = 0; k < p.K; ++k) {
       float acc = 0.f;
-      for (int i = 0; i < nc; ++i) acc += vv[i] * st[k * p.C + lane + 32 * i];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) acc += vv[i] * st[k * p.C + lane + 32 * i];
       acc = warp_sum(acc) * inv;
       if (lane == 0) p.score[((long long)b * p.K + k) * p.P + px] = acc;
     }
@@ -368,6 +370,53 @@ __global__ void __launch_bounds__(256) conv3x3_gather_kernel(const Conv3x3Gather
       }
     }
     *reinterpret_cast<uint32_t*>(p.out + pix * p.ldo + tap * p.C + c) = v;
+  }
+}
+
+// Token-major fast path: one thread produces 4 horizontally adjacent output pixels for ALL channels, so the index
+// arithmetic is done once and the channel-contiguous low-res rows are read with 128-bit loads (ldi % 4 == 0).
+__global__ void __launch_bounds__(256) upsample_bilinear_tok_kernel(const UpsampleParams p) {
+  const int W4 = p.W >> 2;
+  const long long total = (long long)p.B * p.H * W4;
+  const float sy = float(p.h) / float(p.H), sx = float(p.w) / float(p.W);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x4 = int(i % W4);
+    const int y = int((i / W4) % p.H);
+    const int b = int(i / ((long long)W4 * p.H));
+    int y0, y1;
+    float ly0, ly1;
+    bilinear_src(y, sy, p.h, y0, y1, ly0, ly1);
+    const float* r0[4]; const float* r1[4]; const float* r2[4]; const float* r3[4];
+    float w00[4], w01[4], w10[4], w11[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int x0, x1;
+      float lx0, lx1;
+      bilinear_src(x4 * 4 + e, sx, p.w, x0, x1, lx0, lx1);
+      const float* base = p.in + (long long)b * p.in_bs;
+      r0[e] = base + (long long)(y0 * p.w + x0) * p.ldi;
+      r1[e] = base + (long long)(y0 * p.w + x1) * p.ldi;
+      r2[e] = base + (long long)(y1 * p.w + x0) * p.ldi;
+      r3[e] = base + (long long)(y1 * p.w + x1) * p.ldi;
+      w00[e] = lx0; w01[e] = lx1; w10[e] = lx0; w11[e] = lx1;
+    }
+    float* obase = p.out + ((long long)b * p.C * p.H + y) * p.W + x4 * 4;
+    for (int c = 0; c < p.C; c += 4) {
+      float o[4][4];  // [channel][pixel]
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 a = *reinterpret_cast<const float4*>(r0[e] + c), bb = *reinterpret_cast<const float4*>(r1[e] + c);
+        const float4 cc = *reinterpret_cast<const float4*>(r2[e] + c), d = *reinterpret_cast<const float4*>(r3[e] + c);
+        o[0][e] = ly0 * (w00[e] * a.x + w01[e] * bb.x) + ly1 * (w10[e] * cc.x + w11[e] * d.x);
+        o[1][e] = ly0 * (w00[e] * a.y + w01[e] * bb.y) + ly1 * (w10[e] * cc.y + w11[e] * d.y);
+        o[2][e] = ly0 * (w00[e] * a.z + w01[e] * bb.z) + ly1 * (w10[e] * cc.z + w11[e] * d.z);
+        o[3][e] = ly0 * (w00[e] * a.w + w01[e] * bb.w) + ly1 * (w10[e] * cc.w + w11[e] * d.w);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c + k < p.C)
+          *reinterpret_cast<float4*>(obase + (long long)(c + k) * p.H * p.W) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+    }
   }
 }
 

@@ -219,28 +219,49 @@ class VitEncoder {
       LayerNormParams l2{x, D, lw.ln2_g, lw.ln2_b, 1e-5f, L.M, D, nullptr, 0, hbuf, (long long)D * s, cfg.precise, D};
       launch_layernorm(l2, st); ++n;
       run_gemm(layer_plans_[li].fc, st); ++n;
-      run_gemm(layer_plans_[li].proj, st); ++n;
-
       // ---- feature taps (models.py:568-582) ----
       while (tap_i < outs.taps.size() && outs.taps[tap_i].layer < li) ++tap_i;
       const bool last = li == cfg.layers - 1;
+      // the bf16 token-major tap of a non-final layer is written by the c_proj epilogue itself (second output)
+      __nv_bfloat16* fused_tap = nullptr;
+      if (!last && !cfg.precise)
+        for (size_t t = tap_i; t < outs.taps.size() && outs.taps[t].layer == li; ++t)
+          if (outs.taps[t].tokens_bf16 && !fused_tap) fused_tap = outs.taps[t].tokens_bf16;
+      if (fused_tap) {
+        GemmPlan pl = layer_plans_[li].proj;
+        pl.p.out_bf16 = fused_tap;
+        pl.p.ldcb = D;
+        run_gemm(pl, st); ++n;
+      } else {
+        run_gemm(layer_plans_[li].proj, st); ++n;
+      }
       bool lnp_done = false;
+      for (size_t t = tap_i; t < outs.taps.size() && outs.taps[t].layer == li; ++t) {
+        const VitTap& tp = outs.taps[t];
+        const float* src = x;
+        if (last) {
+          if (!lnp_done) {  // ln_post once; its bf16 copy (if wanted) comes out of the same kernel
+            LayerNormParams lq{x, D, weights.ln_post_g, weights.ln_post_b, 1e-5f, L.M, D, lnp, D, tp.tokens_bf16, D, 0, 0};
+            launch_layernorm(lq, st); ++n;
+            lnp_done = true;
+            src = lnp;
+            if (tp.nchw) { launch_tap_nchw(src, tp.nchw, B, L.Ntok, D, st); ++n; }
+            continue;
+          }
+          src = lnp;
+        }
+        if (tp.nchw) { launch_tap_nchw(src, tp.nchw, B, L.Ntok, D, st); ++n; }
+        if (tp.tokens_bf16 && tp.tokens_bf16 != fused_tap) {
+          CastParams cp{src, D, tp.tokens_bf16, D, L.M, D, 0, 0, 1.0f};
+          cast_bf16_kernel<<<148 * 8, 256, 0, st>>>(cp); ++n;
+        }
+      }
       auto ensure_lnp = [&] {
         if (lnp_done) return;
         LayerNormParams lq{x, D, weights.ln_post_g, weights.ln_post_b, 1e-5f, L.M, D, lnp, D, nullptr, 0, 0, 0};
         launch_layernorm(lq, st); ++n;
         lnp_done = true;
       };
-      for (size_t t = tap_i; t < outs.taps.size() && outs.taps[t].layer == li; ++t) {
-        const VitTap& tp = outs.taps[t];
-        const float* src = x;
-        if (last) { ensure_lnp(); src = lnp; }
-        if (tp.nchw) { launch_tap_nchw(src, tp.nchw, B, L.Ntok, D, st); ++n; }
-        if (tp.tokens_bf16) {
-          CastParams cp{src, D, tp.tokens_bf16, D, L.M, D, 0, 0, 1.0f};
-          cast_bf16_kernel<<<148 * 8, 256, 0, st>>>(cp); ++n;
-        }
-      }
       if (last && outs.last_tokens_f32) {
         ensure_lnp();
         DCLIP_CHECK_CUDA(cudaMemcpyAsync(outs.last_tokens_f32, lnp, size_t(L.M) * D * 4, cudaMemcpyDeviceToDevice, st));
