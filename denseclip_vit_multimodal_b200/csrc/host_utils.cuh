@@ -6,6 +6,7 @@
 #include <cudaTypedefs.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -234,14 +235,23 @@ inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
   return plan;
 }
 
-inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
+template <bool PT>
+inline void run_attn_variant(const AttnPlan& plan, cudaStream_t stream) {
+  using Cfg = AttnCfgT<PT>;
   static bool attr_set = false;
   if (!attr_set) {
-    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg::SMEM_BYTES));
+    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  attn_fwd_tcgen05_kernel<<<plan.grid, AttnCfg::THREADS, AttnCfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.p);
+  attn_fwd_tcgen05_kernel<PT><<<plan.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.p);
   DCLIP_CHECK_CUDA(cudaGetLastError());
+}
+
+// P in TMEM (TS MMA) is the production variant; the shared-memory P variant is kept for A/B checks (DCLIP_ATTN_P_SMEM=1)
+inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
+  static const bool p_smem = [] { const char* e = getenv("DCLIP_ATTN_P_SMEM"); return e && e[0] == '1'; }();
+  if (p_smem) run_attn_variant<false>(plan, stream);
+  else run_attn_variant<true>(plan, stream);
 }
 
 template <int QB>

@@ -125,6 +125,36 @@ int main(int argc, char** argv) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, 0) != cudaSuccess) { printf("no CUDA device\n"); return 3; }
   printf("device: %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+  if (argc > 4 && !strcmp(argv[1], "timeline")) {
+    const int B = atoi(argv[2]), H = atoi(argv[3]), N = atoi(argv[4]);
+    const int D = H * 64, ld = 3 * D;
+    __nv_bfloat16 *qkv, *out;
+    long long* dbg;
+    cudaMalloc(&qkv, size_t(B) * N * ld * 2); cudaMalloc(&out, size_t(B) * N * D * 2); cudaMalloc(&dbg, 1024 * 8);
+    fill_bf16<<<(size_t(B) * N * ld + 255) / 256, 256>>>(qkv, size_t(B) * N * ld, 11u, 2.0f);
+    AttnOperands op{qkv, qkv, qkv, ld, ld, ld, (long long)N * ld, (long long)N * ld, (long long)N * ld, N};
+    AttnParams p{};
+    p.B = B; p.H = H; p.Nq_total = N; p.q_start = 1; p.Nk = N; p.q_col0 = 0; p.k_col0 = D; p.v_col0 = 2 * D;
+    p.scale_log2 = 0.125f * 1.4426950408889634f; p.out = out; p.out_batch_stride = (long long)N * D; p.ldo = D;
+    for (int rep = 0; rep < 2; ++rep) {
+      cudaMemset(dbg, 0, 1024 * 8);
+      p.dbg = dbg; p.dbg_cta = rep == 0 ? 0 : 700;
+      AttnPlan plan = make_attn_plan(op, p);
+      run_attn(plan, 0);
+      cudaDeviceSynchronize();
+      std::vector<long long> h(1024);
+      cudaMemcpy(h.data(), dbg, 1024 * 8, cudaMemcpyDeviceToHost);
+      long long t0 = h[6];
+      printf("timeline CTA %d (cycles rel. to first wait)  cols: wait_start s_full_got ld_done max_done exps_done o_done_got arrived | mma: pv_issue qk_issue\n", p.dbg_cta);
+      for (int j = 0; j < 17; ++j)
+        for (int i = 0; i < 2; ++i) {
+          const long long* d = &h[(i * 32 + j) * 8];
+          printf("wg%d j=%2d  %7lld %7lld %7lld %7lld %7lld %7lld %7lld | %7lld %7lld\n", i, j, d[6] - t0, d[0] - t0, d[1] - t0, d[2] - t0,
+                 d[3] - t0, d[4] ? d[4] - t0 : 0, d[5] - t0, h[512 + (i * 32 + j) * 2] - t0, h[512 + (i * 32 + j) * 2 + 1] ? h[512 + (i * 32 + j) * 2 + 1] - t0 : 0);
+        }
+    }
+    return 0;
+  }
   if (argc > 4 && !strcmp(argv[1], "prof")) {
     run_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), 2.0f, true, true);
     return g_fail ? 1 : 0;

@@ -346,9 +346,10 @@ class VitEncoder {
       AttnOperands op{qkv, qkv, qkv, 3 * D, 3 * D, 3 * D, bs, bs, bs, L.Ntok};
       AttnParams p{};
       p.B = B; p.H = cfg.heads; p.Nq_total = L.Ntok; p.Nk = L.Ntok;
-      // N = 1 + 256k (512x1024 and 512x512 at ps 16): start the tensor-core kernel at row 1 and give the CLS query to
-      // the side kernel, so every CTA owns a full 256-row block
-      p.q_start = (L.Ntok > 1 && (L.Ntok - 1) % 256 == 0) ? 1 : 0;
+      // All query rows (CLS included) go through the tensor-core kernel.  (Measured on B200: peeling the CLS query
+      // off into the few-query kernel so that N - 1 = 8 x 256 rows tile exactly was slower, 0.370 vs 0.343 ms/layer at
+      // B = 16, because the side kernel is latency-bound; see profiles/r01_attention_notes.md.)
+      p.q_start = 0;
       p.q_col0 = 0; p.k_col0 = D; p.v_col0 = 2 * D;
       p.scale_log2 = 0.125f * 1.4426950408889634f;
       p.out = hbuf; p.out_batch_stride = (long long)L.Ntok * D; p.ldo = D;
