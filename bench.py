@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="launch kernels eagerly instead of replaying a captured graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,6 +191,8 @@ def main():
     model = D.DenseCLIP(**copy.deepcopy(model_kwargs()), precision=args.precision)
     init_uninitialised(model)
     model = model.eval().to(dev)
+    if not args.no_cuda_graph:
+        model.enable_cuda_graph(True)
     B, H, W = args.batch, args.height, args.width
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
     host_imgs = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(2)]
@@ -222,6 +225,8 @@ def main():
             e1.record()
             barrier()
         launches = _lib.launch_count(local)
+        if not args.no_cuda_graph:  # replays do not pass through the C ABI: count = kernels captured per step x steps
+            launches = int(getattr(model, "graph_launches_per_step", 0)) * args.steps
         ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
         assert out["seg"].shape == (B, 19, H, W) and out["depth"].shape == (B, 1, H, W)
         del out
@@ -315,7 +320,7 @@ def main():
             "metric": METRIC, "value": total_imgs_per_s, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "bf16x3-split (fp32-class)", "data": "synthetic",
-            "config": {"workload": workload_name(args), "global_batch": world * B, "image": [H, W], "parallelism": f"dp{world} (batch sharded by image)",
+            "config": {"workload": workload_name(args), "cuda_graph": not args.no_cuda_graph, "global_batch": world * B, "image": [H, W], "parallelism": f"dp{world} (batch sharded by image)",
                        "l2": "no explicit flush: each step streams ~4 GB of activations per GPU (>> 126 MB L2) and alternates 2 input batches"},
             "clocks": clocks,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -240,14 +240,19 @@ class DenseCLIP(nn.Module):
         return p
 
     def _text_embeddings(self, B: int, device):
-        texts = self.texts.to(device)
-        if isinstance(self.text_encoder, CLIPTextContextEncoder) and self.contexts is not None:
-            t = self.text_encoder(texts, self.contexts)          # [1, K, C], cached per weight version
-        elif isinstance(self.text_encoder, CLIPTextEncoder):
-            t = self.text_encoder(texts).unsqueeze(0)            # [1, K, C]
-        else:
-            raise TypeError("unsupported text encoder")
-        return t.expand(B, -1, -1).contiguous()
+        """Class text embeddings [B, K, C].  Input-independent (weights-only), so the [1, K, C] result is cached per
+        parameter version; the per-forward cost is an expand."""
+        ver = (_param_versions(self.text_encoder), None if self.contexts is None else (self.contexts.data_ptr(), self.contexts._version),
+               str(device))
+        if getattr(self, "_text_cache", None) is None or self._text_cache[0] != ver:
+            if isinstance(self.text_encoder, CLIPTextContextEncoder) and self.contexts is not None:
+                t = self.text_encoder(self.texts, self.contexts)          # [1, K, C]
+            elif isinstance(self.text_encoder, CLIPTextEncoder):
+                t = self.text_encoder(self.texts).unsqueeze(0)            # [1, K, C]
+            else:
+                raise TypeError("unsupported text encoder")
+            self._text_cache = (ver, t)
+        return self._text_cache[1].expand(B, -1, -1).contiguous()
 
     def _tail_native(self, tokens: torch.Tensor, gh: int, gw: int):
         """tokens: fp32 [B, 1+P, Cb] (final-layer features, CLS at row 0). Returns (text_embeddings [B,K,C],
@@ -324,7 +329,46 @@ class DenseCLIP(nn.Module):
         written."""
         return self.forward(img, return_loss=False, _class_map=True)
 
+    # ---- CUDA graph replay (opt-in) ----
+    def enable_cuda_graph(self, flag: bool = True):
+        """Capture the inference forward (per input shape) into a CUDA graph and replay it: removes the host-side launch
+        cost of the ~190 kernels of one step.  Outputs are then STATIC buffers, overwritten by the next call."""
+        self._use_graph = bool(flag)
+        self._graphs = {}
+        return self
+
+    def _graph_forward(self, img, class_map: bool):
+        ver = (_param_versions(self), self.precision, self.training)
+        key = (tuple(img.shape), img.device.index, class_map)
+        ent = self._graphs.get(key)
+        if ent is None or ent["ver"] != ver:
+            static_in = img.detach().clone().float().contiguous()
+            cur = torch.cuda.current_stream(img.device)
+            side = torch.cuda.Stream(device=img.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up outside capture: packs weights, builds plans, sizes the workspace
+                for _ in range(2):
+                    self._forward_impl(static_in, None, False, {'_class_map': class_map})
+            cur.wait_stream(side)
+            torch.cuda.synchronize(img.device)
+            dev = img.device.index if img.device.index is not None else torch.cuda.current_device()
+            n0 = _lib.launch_count(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_impl(static_in, None, False, {'_class_map': class_map})
+            ent = dict(ver=ver, graph=graph, inp=static_in, out=out, launches=_lib.launch_count(dev) - n0)
+            self._graphs = {key: ent}  # one live graph: its private pool holds a full set of activations
+        ent["inp"].copy_(img, non_blocking=True)
+        ent["graph"].replay()
+        self.graph_launches_per_step = ent["launches"]
+        return ent["out"]
+
     def forward(self, img, img_metas=None, gt_semantic_seg=None, return_loss=True, **kwargs):
+        if getattr(self, "_use_graph", False) and not (return_loss and self.training) and img.is_cuda:
+            return self._graph_forward(img, bool(kwargs.get('_class_map', False)))
+        return self._forward_impl(img, gt_semantic_seg, return_loss, kwargs)
+
+    def _forward_impl(self, img, gt_semantic_seg, return_loss, kwargs):
         """Reference denseclip.py:702-916.  Inference returns {'seg': [B,K,H,W], 'depth': [B,1,H,W]} fp32; the training
         branch returns {'main_output','depth_output','aux_losses'} resized to the ground-truth size.  Forward-only:
         the native path carries no autograd graph (backward of the trainable tail is out of scope)."""

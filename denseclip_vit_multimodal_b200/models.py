@@ -450,7 +450,7 @@ class CLIPTextEncoder(_TextTowerBase):
             self.apply(self._init_weights_default)
 
     def forward(self, text):
-        key = (_param_versions(self), tuple(text.flatten().tolist()))
+        key = (_param_versions(self), tuple(text.cpu().flatten().tolist()))
         if self._cache.get("key") == key:
             return self._cache["val"]
         K, L = text.shape
@@ -458,7 +458,7 @@ class CLIPTextEncoder(_TextTowerBase):
         emb = self.token_embedding.weight.detach().index_select(0, text.reshape(-1).to(dev))  # row gather
         pos = _f32(self.positional_embedding)[:L]
         x = ops.gamma_residual(pos.repeat(K, 1), torch.ones(1, device=dev), _f32(emb))  # emb + pos
-        out = self._encode(x, K, L, text.argmax(dim=-1))
+        out = self._encode(x, K, L, text.cpu().argmax(dim=-1))
         self._cache = {"key": key, "val": out}
         return out
 
@@ -480,7 +480,7 @@ class CLIPTextContextEncoder(_TextTowerBase):
             self._load_clip_text(pretrained)
 
     def forward(self, text, context):
-        key = (_param_versions(self), context.data_ptr(), context._version, tuple(text.flatten().tolist()))
+        key = (_param_versions(self), context.data_ptr(), context._version, tuple(text.cpu().flatten().tolist()))
         if self._cache.get("key") == key:
             return self._cache["val"]
         dev = self.token_embedding.weight.device
@@ -495,7 +495,7 @@ class CLIPTextContextEncoder(_TextTowerBase):
         seq[:, :, 1 + N2:] = emb[None, :, 1:]
         pos = _f32(self.positional_embedding)
         x = ops.gamma_residual(pos.repeat(Bc * K, 1), torch.ones(1, device=dev), seq.view(-1, Cw))
-        eos = (text.argmax(dim=-1) + N2).reshape(1, K).expand(Bc, K).reshape(-1)
+        eos = (text.cpu().argmax(dim=-1) + N2).reshape(1, K).expand(Bc, K).reshape(-1)
         out = self._encode(x, Bc * K, L, eos).view(Bc, K, self.embed_dim)
         self._cache = {"key": key, "val": out}
         return out
