@@ -197,14 +197,14 @@ def score_map(vis: torch.Tensor, row0: int, P: int, text: torch.Tensor, eps: flo
 
 def upsample_bilinear(x: torch.Tensor, size, *, tokens_hw=None, channels=None) -> torch.Tensor:
     """Bilinear (align_corners=False) resize to `size`. x: NCHW fp32, or token-major fp32 [B, h*w, ld] with tokens_hw."""
-    x = _req(x, torch.float32, "x")
     H, W = size
     if tokens_hw is None:
-        x = x.contiguous()
+        x = _req(x.contiguous(), torch.float32, "x")
         B, Cc, hh, ww = x.shape
         out = torch.empty(B, Cc, H, W, dtype=torch.float32, device=x.device)
         _call(x, _lib.lib().dclip_upsample_bilinear, _ptr(x), 1, 0, 0, B, Cc, hh, ww, H, W, _ptr(out), _stream(x))
     else:
+        x = _req(x, torch.float32, "x")
         hh, ww = tokens_hw
         B = x.shape[0]
         Cc = channels if channels is not None else x.shape[2]

@@ -1,0 +1,76 @@
+"""GPU, BASELINE-size shapes (ViT-B/16, 512x1024): size-independent properties of the native forward --
+batch independence / shard equality (bit-exact), determinism, fp32-path vs bf16-path agreement on the normalised
+score map (north_star tolerance 2e-2; argmax agreement is reported), CUDA-graph replay equality."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def models():
+    import bench
+    import denseclip_vit_multimodal_b200 as D
+    torch.manual_seed(0)
+    m = D.DenseCLIP(**copy.deepcopy(bench.model_kwargs()), precision="bf16")
+    bench.init_uninitialised(m)
+    with torch.no_grad():
+        m.gamma.fill_(0.3)   # so that the ContextDecoder visibly contributes to the score map
+    m = m.eval().cuda()
+    m32 = D.DenseCLIP(**copy.deepcopy(bench.model_kwargs()), precision="fp32")
+    m32.load_state_dict(m.state_dict())
+    return m, m32.eval().cuda()
+
+
+def test_batch_independence_determinism_and_shard_equality(models):
+    from denseclip_vit_multimodal_b200 import distributed as dd
+    m, _ = models
+    g = torch.Generator(device="cuda").manual_seed(1)
+    img = torch.randn(3, 3, 512, 1024, device="cuda", generator=g)
+    with torch.no_grad():
+        full = m(img, return_loss=False)
+        again = m(img, return_loss=False)
+        assert torch.equal(full["seg"], again["seg"]) and torch.equal(full["depth"], again["depth"])   # deterministic
+        parts = [m(dd.shard_batch(img, 2, r), return_loss=False) for r in range(2)]                    # 2-way image shard
+    seg = torch.cat([p["seg"] for p in parts]); depth = torch.cat([p["depth"] for p in parts])
+    assert torch.equal(seg, full["seg"]) and torch.equal(depth, full["depth"])   # bit-exact: no cross-image op anywhere
+    assert full["seg"].shape == (3, 19, 512, 1024) and torch.isfinite(full["seg"]).all()
+
+
+def test_bf16_path_against_fp32_path_on_score_map(models):
+    m, m32 = models
+    g = torch.Generator(device="cuda").manual_seed(2)
+    img = torch.randn(2, 3, 512, 1024, device="cuda", generator=g)
+    with torch.no_grad():
+        o16 = m(img, return_loss=False); s16 = m.last_score_map.clone()
+        o32 = m32(img, return_loss=False); s32 = m32.last_score_map.clone()
+    assert float(s32.abs().max()) <= 1.0 + 1e-5                       # cosine similarities
+    max_abs = float((s16 - s32).abs().max())
+    agree = float((s16.argmax(1) == s32.argmax(1)).float().mean())
+    top2 = s32.topk(2, dim=1).values
+    gap = top2[:, 0] - top2[:, 1]
+    clear = gap > 4 * max_abs                                          # pixels whose fp32 top-2 gap exceeds the bf16 noise
+    agree_clear = float((s16.argmax(1) == s32.argmax(1))[clear].float().mean()) if clear.any() else 1.0
+    seg_agree = float((o16["seg"].argmax(1) == o32["seg"].argmax(1)).float().mean())
+    print(f"score-map bf16 vs fp32-path: max_abs={max_abs:.2e} argmax_agree={agree:.4f} "
+          f"agree_where_gap>4*err={agree_clear:.4f} ({float(clear.float().mean()):.3f} of pixels) seg_argmax_agree={seg_agree:.4f}")
+    assert max_abs <= 2e-2                                             # north_star bf16 tolerance on the normalised score map
+    assert agree_clear >= 0.999
+
+
+def test_cuda_graph_replay_matches_eager(models):
+    m, _ = models
+    g = torch.Generator(device="cuda").manual_seed(3)
+    imgs = [torch.randn(2, 3, 512, 1024, device="cuda", generator=g) for _ in range(2)]
+    with torch.no_grad():
+        eager = [m(i, return_loss=False)["seg"].clone() for i in imgs]
+        m.enable_cuda_graph(True)
+        try:
+            for i, e in zip(imgs, eager):
+                assert torch.equal(m(i, return_loss=False)["seg"], e)
+            pm = m.predict(imgs[0])
+            assert torch.equal(pm["seg"].long(), eager[0].argmax(1))
+        finally:
+            m.enable_cuda_graph(False)

@@ -1,0 +1,146 @@
+"""GPU: each native kernel, through the C ABI, against a plain PyTorch fp32 evaluation of the same op on the same
+(bf16-rounded where applicable) inputs.  Covers ragged / tail / single-row edge cases."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from denseclip_vit_multimodal_b200 import ops as o
+    return o
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, device="cuda", generator=g) * scale
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 64, 64), (130, 200, 192), (1000, 768, 768), (257, 2304, 768), (4099, 512, 1024)])
+def test_gemm_bf16_bias_act_residual(ops, M, N, K):
+    a, w, b, r = _rand(M, K, seed=1), _rand(N, K, scale=K ** -0.5, seed=2), _rand(N, seed=3), _rand(M, N, seed=4)
+    ab, wb = a.bfloat16(), w.bfloat16()
+    ref = ab.float() @ wb.float().t() + b
+    out, _ = ops.gemm(ab, wb, bias=b, want_f32=True)
+    assert rel_err(out, ref) < 2e-5
+    _, ob = ops.gemm(ab, wb, bias=b, act="quickgelu", want_bf16=True)
+    assert rel_err(ob, ref * torch.sigmoid(1.702 * ref)) < 1.2e-2            # bf16 output rounding + tanh.approx
+    x = r.clone()
+    ops.gemm(ab, wb, bias=b, residual=x, out_f32=x)                          # in-place residual stream update
+    assert rel_err(x, ref + r) < 2e-5
+    o32, o16 = ops.gemm(ab, wb, bias=b, act="relu", want_f32=True, want_bf16=True)
+    assert rel_err(o32, F.relu(ref)) < 2e-5 and rel_err(o16, F.relu(ref)) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(19, 256, 256), (300, 512, 768), (2049, 256, 512)])
+def test_gemm_split_bf16_is_fp32_class(ops, M, N, K):
+    a, w, b = _rand(M, K, seed=5), _rand(N, K, scale=K ** -0.5, seed=6), _rand(N, seed=7)
+    ref = (a.double() @ w.double().t() + b.double()).float()
+    out, _ = ops.gemm(ops.split_bf16(a), ops.split_bf16(w), split_in=True, bias=b, want_f32=True)
+    assert rel_err(out, ref) < 3e-5
+    _, osplit = ops.gemm(ops.split_bf16(a), ops.split_bf16(w), split_in=True, bias=b, act="gelu", want_bf16=True, split_out=True)
+    g = F.gelu(ref)
+    assert rel_err(osplit[:, :N].float() + osplit[:, N:].float(), g) < 3e-5
+
+
+@pytest.mark.parametrize("M,D", [(1, 128), (33, 256), (4098, 768), (77, 1024)])
+def test_layernorm(ops, M, D):
+    x, g, b = _rand(M, D, scale=3, seed=8) + 0.5, _rand(D, seed=9) * 0.1 + 1, _rand(D, seed=10) * 0.1
+    ref = F.layer_norm(x, (D,), g, b, 1e-5)
+    of, ob = ops.layernorm(x, g, b, want_f32=True, want_bf16=True, split=True)
+    assert rel_err(of, ref) < 1e-5
+    assert rel_err(ob[:, :D].float() + ob[:, D:].float(), ref) < 2e-5
+
+
+@pytest.mark.parametrize("B,H,N", [(1, 1, 1), (2, 2, 129), (1, 4, 1025), (2, 12, 2049), (1, 2, 2629)])
+def test_flash_attention_vs_sdpa(ops, B, H, N):
+    D = H * 64
+    qkv = _rand(B, N, 3 * D, scale=1.5, seed=11).bfloat16()
+    out = torch.empty(B, N, D, dtype=torch.bfloat16, device="cuda")
+    ops.attention(qkv, qkv, qkv, B=B, H=H, Nq=N, Nk=N, q_col0=0, k_col0=D, v_col0=2 * D, scale=0.125, out=out)
+    q, k, v = (t.float().view(B, N, H, 64).transpose(1, 2) for t in qkv.split(D, dim=-1))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, D)
+    assert rel_err(out, ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("causal,Nq,Nk", [(False, 19, 19), (False, 19, 2049), (True, 22, 22), (False, 1, 300)])
+def test_attention_small(ops, dtype, causal, Nq, Nk):
+    B, H = 3, 4
+    D = H * 64
+    if causal:
+        x = _rand(B, Nq, 3 * D, seed=12).to(dtype)
+        q, k, v, cols = x, x, x, (0, D, 2 * D)
+    else:
+        q, kv = _rand(B, Nq, D, seed=13).to(dtype), _rand(B, Nk, 2 * D, seed=14).to(dtype)
+        k, v, cols = kv, kv, (0, 0, D)
+    out = torch.empty(B, Nq, D, dtype=torch.float32, device="cuda")
+    ops.attention_small(q, k, v, B=B, H=H, q_first=0, q_count=Nq, Nk=Nk, q_col0=cols[0], k_col0=cols[1], v_col0=cols[2],
+                        scale=0.125, out=out, causal=causal)
+    qq = q[..., cols[0]:cols[0] + D].float().view(B, Nq, H, 64).transpose(1, 2)
+    kk = k[..., cols[1]:cols[1] + D].float().view(B, Nk, H, 64).transpose(1, 2)
+    vv = v[..., cols[2]:cols[2] + D].float().view(B, Nk, H, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qq, kk, vv, is_causal=causal).transpose(1, 2).reshape(B, Nq, D)
+    assert rel_err(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("g0,gh,gw", [(14, 32, 64), (2, 2, 4), (14, 14, 14), (7, 3, 5)])
+def test_posemb_interp(ops, g0, gh, gw):
+    D = 256
+    pos = _rand(1 + g0 * g0, D, seed=15)
+    got = ops.posemb_interp(pos, g0, gh, gw)
+    ref = F.interpolate(pos[1:].reshape(1, g0, g0, D).permute(0, 3, 1, 2), size=(gh, gw), mode="bilinear", align_corners=False)
+    ref = torch.cat([pos[:1], ref.permute(0, 2, 3, 1).reshape(-1, D)])
+    assert rel_err(got, ref) < 1e-6
+
+
+def test_layout_mean_score_upsample(ops):
+    B, gh, gw, C, K = 2, 8, 16, 128, 19
+    tok = _rand(B, 1 + gh * gw, C, seed=16)
+    nchw = ops.tap_nchw(tok, gh, gw)
+    ref_nchw = tok[:, 1:].permute(0, 2, 1).reshape(B, C, gh, gw)
+    assert torch.equal(nchw, ref_nchw)
+    back, _ = ops.nchw_to_tokens(nchw, row_off=1, rows=1 + gh * gw)
+    assert torch.equal(back[:, 1:], tok[:, 1:])
+    assert rel_err(ops.token_mean(tok, 1, gh * gw), tok[:, 1:].mean(1)) < 1e-6
+    text = _rand(B, K, C, seed=17)
+    sm = ops.score_map(tok, 1, gh * gw, text).view(B, K, gh, gw)
+    ref = torch.einsum("bchw,bkc->bkhw", F.normalize(ref_nchw, dim=1), F.normalize(text, dim=2))
+    assert float((sm - ref).abs().max()) < 1e-6
+    low = _rand(B, gh * gw, 20, seed=18)
+    up = ops.upsample_bilinear(low, (gh * 16, gw * 16), tokens_hw=(gh, gw), channels=K)
+    ref_up = F.interpolate(low[..., :K].permute(0, 2, 1).reshape(B, K, gh, gw), size=(gh * 16, gw * 16), mode="bilinear",
+                           align_corners=False)
+    assert rel_err(up, ref_up) < 1e-6
+    assert torch.equal(ops.upsample_argmax(low, (gh * 16, gw * 16), tokens_hw=(gh, gw), channels=K).long(), ref_up.argmax(1))
+    assert rel_err(ops.upsample_bilinear(ref_nchw, (13 * 4, 20)), F.interpolate(ref_nchw, size=(52, 20), mode="bilinear", align_corners=False)) < 1e-6
+
+
+@pytest.mark.parametrize("gh,gw", [(8, 16), (4, 8), (2, 64)])   # implicit-conv TMA path / gather fallback / one-row box
+def test_conv3x3_implicit_gemm(ops, gh, gw):
+    from denseclip_vit_multimodal_b200 import models as M
+    B, C, N = 2, 128, 64
+    x = _rand(B, C, gh, gw, seed=19)
+    w, b = _rand(N, C, 3, 3, scale=(9 * C) ** -0.5, seed=20), _rand(N, seed=21)
+    tok, tokb = ops.nchw_to_tokens(x, row_off=1, rows=1 + gh * gw, f32=True, bf16=True)
+    wp = ops.pack_weight(M.conv3x3_weight_to_gemm(w), False)
+    y, _ = M.conv3x3_tokens(tokb, 1, gh, gw, C, wp, split_in=False, bias=b, act="relu", want_f32=True)
+    ref = F.relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, padding=1)).permute(0, 2, 3, 1).reshape(-1, N)
+    assert rel_err(y, ref) < 2e-5
+
+
+def test_ops_reject_bad_inputs(ops):
+    from denseclip_vit_multimodal_b200 import DclipError
+    a = torch.zeros(4, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(DclipError):
+        ops.gemm(a, torch.zeros(6, 64, dtype=torch.bfloat16, device="cuda"), want_f32=True)      # N % 4 != 0
+    with pytest.raises(DclipError):
+        ops.gemm(a.float(), a, want_f32=True)                                                     # wrong dtype
+    with pytest.raises(DclipError):
+        ops.layernorm(torch.zeros(2, 100, device="cuda"), torch.ones(100, device="cuda"), torch.zeros(100, device="cuda"), want_f32=True)
