@@ -42,10 +42,12 @@ struct GemmParams {
   // implicit 3x3 / pad-1 convolution (conv_C > 0): A is a token-major image [B][gh][gw][C(x2 if split_in)] read through a
   // 4D tensor map; K = 9*C ordered (ky, kx, c); M = B*gh*gw with 128-pixel tiles that never straddle an image.
   int conv_C, conv_gw, conv_tiles_per_img;
+  int cluster;   // 2: CTA pairs (cluster 2x1x1) share every W tile -- each CTA loads half of it and TMA-multicasts it to both
+  int dbg_mode;  // selftest only: 1 = epilogue drains TMEM but skips staging and stores; 2 = stage but skip global stores
 };
 
 // Compile-time epilogue specialisation. ACT < 0 / FLAGS < 0 select the generic (runtime-checked) epilogue.
-enum GemmEpiFlags : int { EPI_RESID = 1, EPI_OUT_F32 = 2, EPI_OUT_BF16 = 4, EPI_SPLIT = 8, EPI_REMAP = 16 };
+enum GemmEpiFlags : int { EPI_RESID = 1, EPI_OUT_F32 = 2, EPI_OUT_BF16 = 4, EPI_SPLIT = 8, EPI_REMAP = 16, EPI_TMA_STORE = 32 };
 
 template <int BN>
 struct GemmCfg {
@@ -84,7 +86,7 @@ __device__ __forceinline__ float apply_act_t(float x, int act_rt) {
 template <int BN, int ACT, int FLAGS>
 __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -97,7 +99,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  // cluster mode: the two CTAs of a pair work on m-blocks (2*mp, 2*mp + 1) of the same n-block in lock step
+  const int cl = p.cluster == 2 ? 2 : 1;
+  const int crank = cl == 2 ? int(cluster_ctarank()) : 0;
+  const int num_units = cl == 2 ? ((num_m + 1) / 2) * num_n : num_m * num_n;  // work items per CTA stream
+  const int unit0 = cl == 2 ? blockIdx.x / 2 : blockIdx.x;
+  const int unit_step = cl == 2 ? gridDim.x / 2 : gridDim.x;
+  const int num_tiles = num_units;
   const int kseg = (p.K + BK - 1) / BK;
   const int num_k = p.split_in ? 3 * kseg : kseg;
 
@@ -110,7 +118,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], cl);   // cluster mode: both CTAs' MMA threads release a stage (its W half lives in both)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -124,6 +132,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (cl == 2) cluster_sync_all();  // peer barriers must be initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -132,8 +141,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+        const int m_blk = (tile / num_n) * cl + crank, n_blk = tile % num_n;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -154,7 +163,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], a_col, m_blk * BM);
           }
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], b_col, n_blk * BN);
+          if (cl == 2)
+            tma_load_2d_mcast(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], b_col,
+                              n_blk * BN + crank * (BN / 2), uint16_t(3));
+          else
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], b_col, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -164,7 +177,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
     int stage = 0;
     uint32_t phase = 0, it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       mbar_wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
@@ -181,7 +194,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             umma_ss_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (cl == 2) umma_commit_mcast(&empty_bar[stage], uint16_t(3));
+          else umma_commit(&empty_bar[stage]);
           if (kb == num_k - 1) umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
@@ -202,8 +216,63 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int sub = lane >> 3;      // row within a group of 4 rows handled per warp instruction
     const int cq = lane & 7;        // 4-column group within the 32-column chunk
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    if constexpr (FLAGS >= 0 && (FLAGS & EPI_TMA_STORE)) {
+      // bf16 output through TMA stores: each warp converts its 32 rows x 64 columns (bias + activation applied in the
+      // row-per-lane TMEM layout), writes them as one SWIZZLE_128B smem tile and hands it to the TMA engine, which
+      // emits full 128 B lines asynchronously (no LSU store traffic, M/N tails clipped by the tensor map).
+      for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
+        const int m_blk = (tile / num_n) * cl + crank, n_blk = tile % num_n;
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        const int row0 = m_blk * BM + q * 32;
+        mbar_wait(&tfull_bar[as], aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cg = half; cg < BN / 64; cg += 2) {
+          const int c0 = n_blk * BN + cg * 64;
+          if (lane == 0) tma_store_wait_read();  // the previous store of this warp has finished reading the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int sc = 0; sc < 2; ++sc) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + as * BN + cg * 64 + sc * 32 + (uint32_t(q * 32) << 16), r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
+              const int c = c0 + sc * 32 + 8 * j;
+              if (p.bias) {
+                if (c < p.N) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                  v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                }
+                if (c + 4 < p.N) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+                  v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = apply_act_t<ACT>(v[e], p.act) * p.out_scale;
+              *reinterpret_cast<uint4*>(stg + lane * 128 + (((sc * 4 + j) ^ (lane & 7)) << 4)) =
+                  make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && c0 < p.N) {
+            tma_store_2d(&tmC, stg, c0, p.dbg_mode == 5 ? (row0 & 4095) : row0);
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else
+    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
+      const int m_blk = (tile / num_n) * cl + crank, n_blk = tile % num_n;
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       const int row0 = m_blk * BM + q * 32;
       const int rows_valid = min(32, p.M - row0);  // may be <= 0
@@ -239,13 +308,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + as * BN + chunk * 32 + (uint32_t(q * 32) << 16), r);
         tmem_wait_ld();
+        if (p.dbg_mode == 1) continue;
         // row-per-lane -> staging (16B chunk j of row `lane` lands at physical chunk j ^ (lane & 7))
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
               make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
-        if (col_ok) {
+        if (col_ok && p.dbg_mode != 2) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int i = 4 * k + sub;
@@ -277,6 +347,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   tc_fence_before();
   __syncthreads();
+  if (cl == 2) cluster_sync_all();  // neither CTA may exit while its peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

@@ -115,7 +115,9 @@ struct GemmOperands {
 // A GEMM launch with its tensor maps pre-encoded (cuTensorMapEncodeTiled is a driver call; plans are built once per
 // (buffer, shape) and replayed, which also makes the forward CUDA-graph capturable without host work).
 struct GemmPlan {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;   // tmC: bf16 output map for the TMA-store epilogue (valid iff tma_store)
+  bool tma_store = false;
+  const void* tma_store_ptr = nullptr;
   GemmParams p;
   int bn = 0;
   int grid = 0;
@@ -130,7 +132,21 @@ inline void launch_gemm_inst(const GemmPlan& plan, cudaStream_t stream) {
     DCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<plan.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmA, plan.tmB, plan.p);
+  if (plan.p.cluster == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(plan.grid);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DCLIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, plan.tmA, plan.tmB, plan.tmC, plan.p));
+  } else {
+    kern<<<plan.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.p);
+  }
   DCLIP_CHECK_CUDA(cudaGetLastError());
 }
 
@@ -140,6 +156,11 @@ inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
   const int flags = (p.residual ? EPI_RESID : 0) | (p.out_f32 ? EPI_OUT_F32 : 0) | (p.out_bf16 ? EPI_OUT_BF16 : 0) |
                     (p.split_out ? EPI_SPLIT : 0) | (p.remap_P > 0 ? EPI_REMAP : 0);
   // hot ViT-block epilogues get compile-time specialisations; everything else takes the generic instantiation
+  if (plan.tma_store && flags == EPI_OUT_BF16 && p.out_bf16 == plan.tma_store_ptr) {
+    if (p.act == ACT_NONE) return launch_gemm_inst<BN, ACT_NONE, EPI_OUT_BF16 | EPI_TMA_STORE>(plan, stream);
+    if (p.act == ACT_QUICKGELU) return launch_gemm_inst<BN, ACT_QUICKGELU, EPI_OUT_BF16 | EPI_TMA_STORE>(plan, stream);
+    if (p.act == ACT_RELU) return launch_gemm_inst<BN, ACT_RELU, EPI_OUT_BF16 | EPI_TMA_STORE>(plan, stream);
+  }
   if (p.act == ACT_NONE && flags == EPI_OUT_BF16) return launch_gemm_inst<BN, ACT_NONE, EPI_OUT_BF16>(plan, stream);
   if (p.act == ACT_QUICKGELU && flags == EPI_OUT_BF16) return launch_gemm_inst<BN, ACT_QUICKGELU, EPI_OUT_BF16>(plan, stream);
   if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32))
@@ -178,10 +199,34 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
   } else {
     plan.tmA = make_tmap_2d_bf16(op.A, p.M, kcols, op.lda, 128);
   }
-  plan.tmB = make_tmap_2d_bf16(op.W, p.N, kcols, op.ldw, bn);
+  // CTA-pair mode (W tile multicast): worthwhile when there are enough m-blocks to pair up; each CTA loads bn/2 W rows
+  static const int cluster_env = [] { const char* e = getenv("DCLIP_GEMM_CLUSTER"); return e ? atoi(e) : -1; }();
+  const int num_m_blocks = (p.M + 127) / 128;
+  bool use_cluster = bn >= 128 && p.conv_C == 0 && ((num_m_blocks + 1) / 2) * ((p.N + bn - 1) / bn) >= sm_count();
+  if (cluster_env == 0) use_cluster = false;
+  if (cluster_env == 2 && bn >= 128 && num_m_blocks >= 2) use_cluster = true;
+  plan.p.cluster = use_cluster ? 2 : 1;
+  plan.tmB = make_tmap_2d_bf16(op.W, p.N, kcols, op.ldw, use_cluster ? bn / 2 : bn);
+  memset(&plan.tmC, 0, sizeof(plan.tmC));
+  static const bool no_tma_store = [] { const char* e = getenv("DCLIP_GEMM_NO_TMA_STORE"); return e && e[0] == '1'; }();
+  if (!no_tma_store && p.out_bf16 && !p.out_f32 && !p.residual && !p.split_out && p.remap_P == 0 && p.ldcb % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0 && (p.dbg_mode == 0 || p.dbg_mode == 5)) {
+    uint64_t dims[2] = {uint64_t(p.N), uint64_t(p.M)};
+    uint64_t str[1] = {uint64_t(p.ldcb) * 2};
+    uint32_t box[2] = {64, 32};
+    plan.tmC = make_tmap_bf16(p.out_bf16, 2, dims, str, box);
+    plan.tma_store = true;
+    plan.tma_store_ptr = p.out_bf16;
+  }
   const int num_tiles = ((p.M + 127) / 128) * ((p.N + bn - 1) / bn);
   plan.grid = num_tiles < sm_count() ? num_tiles : sm_count();
   if (max_ctas > 0 && plan.grid > max_ctas) plan.grid = max_ctas;
+  if (use_cluster) {
+    const int units = ((num_m_blocks + 1) / 2) * ((p.N + bn - 1) / bn);
+    int pairs = sm_count() / 2;
+    if (units < pairs) pairs = units;
+    plan.grid = 2 * pairs;
+  }
   return plan;
 }
 

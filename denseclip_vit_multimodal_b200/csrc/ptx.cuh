@@ -105,6 +105,34 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
       : "memory");
 }
 
+// multicast variant: the box lands at the same smem offset of every CTA in `cta_mask` and completes tx bytes on the
+// mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mcast(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                                  uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// TMA store (smem tile -> global, bulk async group)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, loads
 // ---------------------------------------------------------------------------------------------
@@ -147,6 +175,13 @@ __device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, ui
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// same, but the arrive is multicast to the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
 

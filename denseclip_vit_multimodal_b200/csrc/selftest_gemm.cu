@@ -215,6 +215,29 @@ int main(int argc, char** argv) {
   cudaGetDeviceProperties(&prop, 0);
   printf("device: %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
   bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  if (argc > 1 && !strcmp(argv[1], "dbg")) {  // where does the GEMM time go? (epilogue variants)
+    const int M = 16 * 2049, N = 2304, K = 768;
+    __nv_bfloat16 *A, *W, *Cb;
+    cudaMalloc(&A, size_t(M) * K * 2); cudaMalloc(&W, size_t(N) * K * 2); cudaMalloc(&Cb, size_t(M) * N * 2);
+    fill_bf16<<<(size_t(M) * K + 255) / 256, 256>>>(A, size_t(M) * K, 1u, 2.0f);
+    fill_bf16<<<(size_t(N) * K + 255) / 256, 256>>>(W, size_t(N) * K, 2u, 0.25f);
+    for (int mode = 0; mode < 6; ++mode) {
+      GemmOperands op{A, K, W, K};
+      GemmParams p{};
+      p.M = M; p.N = N; p.K = K; p.out_scale = 1.f; p.out_bf16 = Cb; p.ldcb = N; p.dbg_mode = mode;
+      if (mode == 3) { p.dbg_mode = 0; p.ldcb = 0; }            // all rows land on one 4.6 KB row: stores hit L2 only
+      if (mode == 4) { p.dbg_mode = 0; p.out_bf16 = nullptr; p.out_f32 = reinterpret_cast<float*>(Cb); p.ldc = 0; }  // fp32 stores, L2 only
+      GemmPlan plan = make_gemm_plan(op, p, 256);
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      for (int i = 0; i < 3; ++i) run_gemm(plan, 0);
+      cudaEventRecord(e0);
+      for (int i = 0; i < 20; ++i) run_gemm(plan, 0);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 20;
+      printf("dbg_mode=%d (0 full, 1 no staging/stores, 2 staging only, 3 bf16 stores to one row, 4 fp32 stores to one row)  %.3f ms  %.1f TFLOP/s\n", mode, ms, 2.0 * M * N * K / ms * 1e-9);
+    }
+    return 0;
+  }
   if (argc > 6 && !strcmp(argv[1], "prof")) {  // prof M N K bn mode  (single shape, for ncu)
     run_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), true);
     return g_fail ? 1 : 0;
