@@ -73,6 +73,7 @@ class GemmArgs(C.Structure):
         ("block_n", C.c_int),
         ("conv_C", C.c_int), ("conv_gw", C.c_int), ("conv_gh", C.c_int), ("conv_B", C.c_int),
         ("a_bs", C.c_longlong),
+        ("conv_G", C.c_int), ("a_gs", C.c_longlong),
     ]
 
 

@@ -106,7 +106,7 @@ int dclip_gemm(dclip_handle_t h, const dclip_gemm_args* a, void* stream) {
     auto it = h->gemm_plans.find(key);
     if (it == h->gemm_plans.end()) {
       GemmOperands op{static_cast<const __nv_bfloat16*>(a->A), int(a->lda), static_cast<const __nv_bfloat16*>(a->W), int(a->ldw)};
-      op.a_bs = a->a_bs; op.conv_B = a->conv_B; op.conv_gh = a->conv_gh;
+      op.a_bs = a->a_bs; op.conv_B = a->conv_B; op.conv_gh = a->conv_gh; op.a_gs = a->a_gs;
       GemmParams p{};
       p.M = a->M; p.N = a->N; p.K = a->K; p.split_in = a->split_in;
       p.bias = a->bias; p.act = a->act; p.out_scale = a->out_scale;
@@ -118,6 +118,7 @@ int dclip_gemm(dclip_handle_t h, const dclip_gemm_args* a, void* stream) {
       if (a->conv_C > 0) {
         p.conv_C = a->conv_C; p.conv_gw = a->conv_gw;
         p.conv_tiles_per_img = a->conv_gh * a->conv_gw / 128;
+        p.conv_G = a->conv_G;
       }
       DCLIP_REQUIRE(p.out_f32 || p.out_bf16, "GEMM needs at least one output");
       if (h->gemm_plans.size() > 4096) h->gemm_plans.clear();

@@ -13,6 +13,12 @@
 #pragma once
 #include "ptx.cuh"
 
+#ifdef DCLIP_GEMM_TIMELINE
+#define DCLIP_GTL(...) __VA_ARGS__
+#else
+#define DCLIP_GTL(...)
+#endif
+
 namespace dclip {
 
 enum GemmAct : int {
@@ -42,18 +48,23 @@ struct GemmParams {
   // implicit 3x3 / pad-1 convolution (conv_C > 0): A is a token-major image [B][gh][gw][C(x2 if split_in)] read through a
   // 4D tensor map; K = 9*C ordered (ky, kx, c); M = B*gh*gw with 128-pixel tiles that never straddle an image.
   int conv_C, conv_gw, conv_tiles_per_img;
-  int cluster;   // 2: CTA pairs (cluster 2x1x1) share every W tile -- each CTA loads half of it and TMA-multicasts it to both
+  int conv_G;    // > 1: grouped conv -- n-block g reads activation group g (5-D map), N = G * BLOCK_N (the neck's 12 taps in one launch)
+  int cluster;   // informational: 2 when launched as CTA pairs (PAIR template), else 1
+  long long* dbg;  // selftest only (-DDCLIP_GEMM_TIMELINE): clock64 stamps of CTA 0's epilogue warp 4 and MMA warp
   int dbg_mode;  // selftest only: 1 = epilogue drains TMEM but skips staging and stores; 2 = stage but skip global stores
 };
 
 // Compile-time epilogue specialisation. ACT < 0 / FLAGS < 0 select the generic (runtime-checked) epilogue.
 enum GemmEpiFlags : int { EPI_RESID = 1, EPI_OUT_F32 = 2, EPI_OUT_BF16 = 4, EPI_SPLIT = 8, EPI_REMAP = 16, EPI_TMA_STORE = 32 };
 
-template <int BN>
+// PAIR: two CTAs of a 2x1x1 cluster form one tcgen05 cta_group::2 unit computing a 256 x BN tile; each CTA stages its
+// own 128 A rows and only HALF of the W tile (BN/2 rows), which cuts the per-SM operand ingest from 48 KB to 32 KB per
+// k-block -- the 1-CTA mainloop is bound by exactly that ingest (profiles/r01_gemm_notes.md).
+template <int BN, bool PAIR = false>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = 196608 / STAGE_BYTES;
   static constexpr int EPI_WARPS = 8;
@@ -83,11 +94,11 @@ __device__ __forceinline__ float apply_act_t(float x, int act_rt) {
   else return apply_act(x, ACT);
 }
 
-template <int BN, int ACT, int FLAGS>
-__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
+template <int BN, int ACT, int FLAGS, bool PAIR = false>
+__global__ void __launch_bounds__(GemmCfg<BN, PAIR>::THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
 
@@ -99,9 +110,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
-  // cluster mode: the two CTAs of a pair work on m-blocks (2*mp, 2*mp + 1) of the same n-block in lock step
-  const int cl = p.cluster == 2 ? 2 : 1;
-  const int crank = cl == 2 ? int(cluster_ctarank()) : 0;
+  // pair mode: the two CTAs of a pair own m-blocks (2*mp, 2*mp + 1) of the same n-block
+  constexpr int cl = PAIR ? 2 : 1;
+  const int crank = PAIR ? int(cluster_ctarank()) : 0;
   const int num_units = cl == 2 ? ((num_m + 1) / 2) * num_n : num_m * num_n;  // work items per CTA stream
   const int unit0 = cl == 2 ? blockIdx.x / 2 : blockIdx.x;
   const int unit_step = cl == 2 ? gridDim.x / 2 : gridDim.x;
@@ -117,22 +128,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], cl);   // cluster mode: both CTAs' MMA threads release a stage (its W half lives in both)
+      mbar_init(&full_bar[s], cl);    // pair mode: leader's producer (with the tx bytes of both CTAs) + the peer's producer
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], Cfg::EPI_WARPS);
+      mbar_init(&tempty_bar[s], Cfg::EPI_WARPS * cl);  // pair mode: the leader's MMA waits for both CTAs' epilogues
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) { tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
-  if (cl == 2) cluster_sync_all();  // peer barriers must be initialised before any multicast lands
+  if constexpr (PAIR) cluster_sync_all();  // peer barriers / TMEM must exist before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -145,7 +156,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int m_blk = (tile / num_n) * cl + crank, n_blk = tile % num_n;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if constexpr (PAIR) {
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            else mbar_arrive_remote(&full_bar[stage], 0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          }
           int a_col = kb * BK, b_col = kb * BK;
           if (p.split_in) {
             const int seg = kb / kseg, off = (kb - seg * kseg) * BK;
@@ -159,22 +175,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int tap = kc / cpb, c0 = (kc - tap * cpb) * BK + (a_col >= p.K ? p.conv_C : 0);
             const int img = m_blk / p.conv_tiles_per_img, p0 = (m_blk - img * p.conv_tiles_per_img) * BM;
             const int y0 = p0 / p.conv_gw, x0 = p0 - y0 * p.conv_gw;
-            tma_load_4d(sa, &tmA, &full_bar[stage], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+            if (p.conv_G > 1) tma_load_5d(sa, &tmA, &full_bar[stage], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img, n_blk);
+            else tma_load_4d(sa, &tmA, &full_bar[stage], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+          } else if constexpr (PAIR) {
+            tma_load_2d_2sm(sa, &tmA, &full_bar[stage], a_col, m_blk * BM);
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], a_col, m_blk * BM);
           }
-          if (cl == 2)
-            tma_load_2d_mcast(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], b_col,
-                              n_blk * BN + crank * (BN / 2), uint16_t(3));
+          if constexpr (PAIR)
+            tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], b_col, n_blk * BN + crank * (BN / 2));
           else
             tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], b_col, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------- MMA issuer ---------------------------------
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+  } else if (warp == 1 && crank == 0) {
+    // ------------------------------- MMA issuer (leader CTA only in pair mode) ----
+    constexpr uint32_t idesc = make_idesc_bf16(BM * cl, BN);
     int stage = 0;
     uint32_t phase = 0, it = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
@@ -192,11 +210,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_ss_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (PAIR) umma_ss_f16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (cl == 2) umma_commit_mcast(&empty_bar[stage], uint16_t(3));
-          else umma_commit(&empty_bar[stage]);
-          if (kb == num_k - 1) umma_commit(&tfull_bar[as]);
+          DCLIP_GTL(if (p.dbg && blockIdx.x == 0 && it < 16 && (kb == 0 || kb == num_k - 1)) p.dbg[256 + it * 2 + (kb ? 1 : 0)] = clock64();)
+          if constexpr (PAIR) {  // both CTAs' producers / epilogues are released by the same commit
+            umma_commit_2sm_mcast(&empty_bar[stage], uint16_t(3));
+            if (kb == num_k - 1) umma_commit_2sm_mcast(&tfull_bar[as], uint16_t(3));
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_k - 1) umma_commit(&tfull_bar[as]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -267,7 +291,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) {
+          if (PAIR && crank != 0) mbar_arrive_remote(&tempty_bar[as], 0);
+          else mbar_arrive(&tempty_bar[as]);
+        }
       }
       if (lane == 0) tma_store_wait_all();
     } else
@@ -289,20 +316,44 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           rrow[k] = p.res_mod ? size_t(1 + pm) : orow[k];
         }
       }
+      // The residual does not depend on the accumulator: its loads for chunk 0 are issued BEFORE waiting for the MMA,
+      // and those of chunk i+1 before chunk i is processed, so the DRAM latency of the fp32 residual stream is hidden.
+      auto load_resid = [&](int chunk, float4 (&dst)[8]) {
+        const int cc = n_blk * BN + chunk * 32 + 4 * cq;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res && chunk < BN / 32 && cc < p.N && 4 * k + sub < rows_valid)
+            dst[k] = *reinterpret_cast<const float4*>(p.residual + rrow[k] * p.ldr + cc);
+        }
+      };
+      // ... and the NEXT tile's residual rows are pulled into L2 now (one tile of lead time): lane = row, 4 lines per lane
+      if (has_res && tile + unit_step < num_tiles) {
+        const int nt = tile + unit_step;
+        const int m2 = ((nt / num_n) * cl + crank) * BM + q * 32 + lane;
+        if (m2 < p.M) {
+          size_t r2 = m2;
+          if (has_remap) {
+            const int bi = m2 / p.remap_P, pm = m2 - bi * p.remap_P;
+            r2 = p.res_mod ? size_t(1 + pm) : size_t(bi) * p.remap_Nt + 1 + pm;
+          }
+          const float* base = p.residual + r2 * p.ldr + (nt % num_n) * BN;
+          for (int ch = half; ch < BN / 32; ch += 2)
+            if ((nt % num_n) * BN + ch * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ch * 32));
+        }
+      }
+      float4 rr[8];
+      load_resid(half, rr);
+      DCLIP_GTL(if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 16) p.dbg[it * 8 + 0] = clock64();)
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
+      DCLIP_GTL(if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 16) p.dbg[it * 8 + 1] = clock64();)
 #pragma unroll 1
       for (int chunk = half; chunk < BN / 32; chunk += 2) {
         const int c = n_blk * BN + chunk * 32 + 4 * cq;
         const bool col_ok = c < p.N;  // N % 4 == 0 is required by the launcher
-        // residual prefetch (issued before the TMEM load so its latency overlaps)
-        float4 rr[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_res && col_ok && 4 * k + sub < rows_valid)
-            rr[k] = *reinterpret_cast<const float4*>(p.residual + rrow[k] * p.ldr + c);
-        }
+        float4 rr_next[8];
+        load_resid(chunk + 2, rr_next);
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias && col_ok) b4 = *reinterpret_cast<const float4*>(p.bias + c);
         uint32_t r[32];
@@ -325,7 +376,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               v.y = apply_act_t<ACT>(v.y + b4.y, p.act) * p.out_scale + rr[k].y;
               v.z = apply_act_t<ACT>(v.z + b4.z, p.act) * p.out_scale + rr[k].z;
               v.w = apply_act_t<ACT>(v.w + b4.w, p.act) * p.out_scale + rr[k].w;
-              if (has_f32) *reinterpret_cast<float4*>(p.out_f32 + orow[k] * p.ldc + c) = v;
+              if (has_f32) {
+                *reinterpret_cast<float4*>(p.out_f32 + orow[k] * p.ldc + c) = v;
+              }
               if (has_b16) {
                 const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
                 *reinterpret_cast<uint2*>(p.out_bf16 + orow[k] * p.ldcb + c) = make_uint2(h0, h1);
@@ -339,18 +392,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
         __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rr[k] = rr_next[k];
+        DCLIP_GTL(if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 16 && chunk < 8) p.dbg[it * 8 + 2 + chunk / 2] = clock64();)
       }
       tc_fence_before();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (PAIR && crank != 0) mbar_arrive_remote(&tempty_bar[as], 0);
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (cl == 2) cluster_sync_all();  // neither CTA may exit while its peer can still multicast into it
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

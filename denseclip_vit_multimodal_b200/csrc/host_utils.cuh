@@ -110,6 +110,7 @@ struct GemmOperands {
   // implicit-conv mode (GemmParams::conv_C > 0): A is [B][row0 + gh*gw][lda] token-major with batch stride a_bs
   long long a_bs = 0;
   int conv_B = 0, conv_gh = 0;
+  long long a_gs = 0;  // grouped conv: element stride between activation groups
 };
 
 // A GEMM launch with its tensor maps pre-encoded (cuTensorMapEncodeTiled is a driver call; plans are built once per
@@ -123,16 +124,16 @@ struct GemmPlan {
   int grid = 0;
 };
 
-template <int BN, int ACT, int FLAGS>
+template <int BN, int ACT, int FLAGS, bool PAIR = false>
 inline void launch_gemm_inst(const GemmPlan& plan, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
   static bool attr_set = false;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, FLAGS>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, FLAGS, PAIR>;
   if (!attr_set) {
     DCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  if (plan.p.cluster == 2) {
+  if (PAIR) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(plan.grid);
     cfg.blockDim = dim3(Cfg::THREADS);
@@ -155,6 +156,20 @@ inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
   const GemmParams& p = plan.p;
   const int flags = (p.residual ? EPI_RESID : 0) | (p.out_f32 ? EPI_OUT_F32 : 0) | (p.out_bf16 ? EPI_OUT_BF16 : 0) |
                     (p.split_out ? EPI_SPLIT : 0) | (p.remap_P > 0 ? EPI_REMAP : 0);
+  // CTA-pair (cta_group::2) instantiations exist for the 256-wide tile and the hot ViT-block epilogues
+  if constexpr (BN == 256) {
+    if (p.cluster == 2) {
+      if (plan.tma_store && flags == EPI_OUT_BF16 && p.out_bf16 == plan.tma_store_ptr) {
+        if (p.act == ACT_NONE) return launch_gemm_inst<BN, ACT_NONE, EPI_OUT_BF16 | EPI_TMA_STORE, true>(plan, stream);
+        if (p.act == ACT_QUICKGELU) return launch_gemm_inst<BN, ACT_QUICKGELU, EPI_OUT_BF16 | EPI_TMA_STORE, true>(plan, stream);
+      }
+      if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32))
+        return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32, true>(plan, stream);
+      if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32 | EPI_OUT_BF16))
+        return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32 | EPI_OUT_BF16, true>(plan, stream);
+      return launch_gemm_inst<BN, -1, -1, true>(plan, stream);
+    }
+  }
   // hot ViT-block epilogues get compile-time specialisations; everything else takes the generic instantiation
   if (plan.tma_store && flags == EPI_OUT_BF16 && p.out_bf16 == plan.tma_store_ptr) {
     if (p.act == ACT_NONE) return launch_gemm_inst<BN, ACT_NONE, EPI_OUT_BF16 | EPI_TMA_STORE>(plan, stream);
@@ -192,19 +207,20 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
     DCLIP_REQUIRE((gh * gw) % 128 == 0 && (128 % gw == 0 || gw % 128 == 0), "implicit conv: grid %dx%d not tileable by 128 pixels", gh, gw);
     DCLIP_REQUIRE(p.M == op.conv_B * gh * gw && p.conv_tiles_per_img == gh * gw / 128, "implicit conv: inconsistent M");
     const uint32_t bw = gw < 128 ? gw : 128, bh = 128 / bw;
-    uint64_t dims[4] = {uint64_t(p.conv_C) * (p.split_in ? 2 : 1), uint64_t(gw), uint64_t(gh), uint64_t(op.conv_B)};
-    uint64_t str[3] = {uint64_t(op.lda) * 2, uint64_t(op.lda) * 2 * gw, uint64_t(op.a_bs) * 2};
-    uint32_t box[4] = {64, bw, bh, 1};
-    plan.tmA = make_tmap_bf16(op.A, 4, dims, str, box);
+    uint64_t dims[5] = {uint64_t(p.conv_C) * (p.split_in ? 2 : 1), uint64_t(gw), uint64_t(gh), uint64_t(op.conv_B), uint64_t(p.conv_G > 1 ? p.conv_G : 1)};
+    uint64_t str[4] = {uint64_t(op.lda) * 2, uint64_t(op.lda) * 2 * gw, uint64_t(op.a_bs) * 2, uint64_t(op.a_gs) * 2};
+    uint32_t box[5] = {64, bw, bh, 1, 1};
+    if (p.conv_G > 1) DCLIP_REQUIRE(p.N == p.conv_G * bn, "grouped conv: N (%d) must equal groups (%d) x BLOCK_N (%d)", p.N, p.conv_G, bn);
+    plan.tmA = make_tmap_bf16(op.A, p.conv_G > 1 ? 5 : 4, dims, str, box);
   } else {
     plan.tmA = make_tmap_2d_bf16(op.A, p.M, kcols, op.lda, 128);
   }
-  // CTA-pair mode (W tile multicast): worthwhile when there are enough m-blocks to pair up; each CTA loads bn/2 W rows
+  // CTA-pair mode (cta_group::2, 256 x 256 tile per pair, each CTA stages half of W): when there are enough pair-units
   static const int cluster_env = [] { const char* e = getenv("DCLIP_GEMM_CLUSTER"); return e ? atoi(e) : -1; }();
   const int num_m_blocks = (p.M + 127) / 128;
-  bool use_cluster = bn >= 128 && p.conv_C == 0 && ((num_m_blocks + 1) / 2) * ((p.N + bn - 1) / bn) >= sm_count();
+  bool use_cluster = bn == 256 && p.conv_C == 0 && ((num_m_blocks + 1) / 2) * ((p.N + bn - 1) / bn) >= sm_count();
   if (cluster_env == 0) use_cluster = false;
-  if (cluster_env == 2 && bn >= 128 && num_m_blocks >= 2) use_cluster = true;
+  if (cluster_env == 2 && bn == 256 && p.conv_C == 0) use_cluster = true;
   plan.p.cluster = use_cluster ? 2 : 1;
   plan.tmB = make_tmap_2d_bf16(op.W, p.N, kcols, op.ldw, use_cluster ? bn / 2 : bn);
   memset(&plan.tmC, 0, sizeof(plan.tmC));

@@ -236,6 +236,48 @@ int main(int argc, char** argv) {
       float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 20;
       printf("dbg_mode=%d (0 full, 1 no staging/stores, 2 staging only, 3 bf16 stores to one row, 4 fp32 stores to one row)  %.3f ms  %.1f TFLOP/s\n", mode, ms, 2.0 * M * N * K / ms * 1e-9);
     }
+#ifdef DCLIP_GEMM_TIMELINE
+    {
+      const int N2 = 768;
+      float* X; cudaMalloc(&X, size_t(M) * N2 * 4); cudaMemset(X, 0, size_t(M) * N2 * 4);
+      long long* dbg; cudaMalloc(&dbg, 512 * 8); cudaMemset(dbg, 0, 512 * 8);
+      GemmOperands op{A, K, W, K};
+      GemmParams p{};
+      p.M = M; p.N = N2; p.K = K; p.out_scale = 1.f; p.out_f32 = X; p.ldc = N2; p.residual = X; p.ldr = N2; p.dbg = dbg;
+      GemmPlan plan = make_gemm_plan(op, p, 256);
+      run_gemm(plan, 0); cudaDeviceSynchronize();
+      cudaMemset(dbg, 0, 512 * 8);
+      run_gemm(plan, 0); cudaDeviceSynchronize();
+      std::vector<long long> h(512);
+      cudaMemcpy(h.data(), dbg, 512 * 8, cudaMemcpyDeviceToHost);
+      long long t0 = h[0];
+      printf("GEMM timeline CTA0 (out-proj shape, cycles): it | epi: wait_start tfull_got chunk0 chunk2 chunk4 chunk6 | mma: first_kb last_kb\n");
+      for (int it = 0; it < 7; ++it)
+        printf("%d | %7lld %7lld %7lld %7lld %7lld %7lld | %7lld %7lld\n", it, h[it * 8] - t0, h[it * 8 + 1] - t0, h[it * 8 + 2] - t0, h[it * 8 + 3] - t0,
+               h[it * 8 + 4] - t0, h[it * 8 + 5] - t0, h[256 + it * 2] - t0, h[256 + it * 2 + 1] - t0);
+    }
+#endif
+    {  // fp32 residual epilogue (out-proj shape): where does the time go?
+      const int N2 = 768;
+      float* X; cudaMalloc(&X, size_t(M) * N2 * 4); cudaMemset(X, 0, size_t(M) * N2 * 4);
+      float* bias; cudaMalloc(&bias, N2 * 4); cudaMemset(bias, 0, N2 * 4);
+      for (int mode = 0; mode < 5; ++mode) {
+        GemmOperands op{A, K, W, K};
+        GemmParams p{};
+        p.M = M; p.N = N2; p.K = K; p.out_scale = 1.f; p.bias = bias; p.out_f32 = X; p.ldc = N2;
+        if (mode != 3) { p.residual = X; p.ldr = N2; }
+        p.dbg_mode = mode == 3 ? 0 : (mode == 4 ? 6 : mode);
+        GemmPlan plan = make_gemm_plan(op, p, 256);
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int i = 0; i < 3; ++i) run_gemm(plan, 0);
+        cudaEventRecord(e0);
+        for (int i = 0; i < 20; ++i) run_gemm(plan, 0);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 20;
+        printf("outproj dbg_mode=%d (0 full st.cs, 1 drain only, 2 no stores, 3 no residual, 4 full plain st)  %.3f ms  %.1f TFLOP/s\n", mode, ms,
+               2.0 * M * N2 * K / ms * 1e-9);
+      }
+    }
     return 0;
   }
   if (argc > 6 && !strcmp(argv[1], "prof")) {  // prof M N K bn mode  (single shape, for ncu)

@@ -295,7 +295,9 @@ class CLIPVisionTransformer(nn.Module):
         ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
         n = len(self.out_indices)
         nchw = [torch.empty(B, self.width, gh, gw, dtype=torch.float32, device=x.device) for _ in range(n)] if taps_nchw else []
-        tok = [torch.empty(B, ntok, self.width, dtype=torch.bfloat16, device=x.device) for _ in range(n)] if taps_tokens_bf16 else []
+        # one contiguous [n_taps, B, Ntok, D] buffer: the neck convolves all taps in a single grouped launch
+        tok_all = torch.empty(n, B, ntok, self.width, dtype=torch.bfloat16, device=x.device) if taps_tokens_bf16 else None
+        tok = [tok_all[i] for i in range(n)] if taps_tokens_bf16 else []
         last = torch.empty(B, ntok, self.width, dtype=torch.float32, device=x.device) if last_tokens else None
         o = _lib.VitOutputs()
         layers_arr = (C.c_int * n)(*self.out_indices)
@@ -309,7 +311,7 @@ class CLIPVisionTransformer(nn.Module):
         stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         _lib.check(st["h"], _lib.lib().dclip_vit_forward(st["vit"], C.c_void_p(x.data_ptr()), B, H, W, C.c_void_p(ws_ptr),
                                                           C.c_size_t(nbytes_of(ws, ws_ptr)), C.byref(o), stream))
-        return dict(nchw=nchw, tokens_bf16=tok, last_tokens=last, grid=(gh, gw))
+        return dict(nchw=nchw, tokens_bf16=tok, tokens_bf16_stacked=tok_all, last_tokens=last, grid=(gh, gw))
 
     def forward(self, x: torch.Tensor):
         """[B,3,H,W] -> list of fp32 [B, width, H//ps, W//ps], one per out_index (reference models.py:543-597)."""
@@ -734,6 +736,9 @@ class ViTFeatureFusionNeck(nn.Module):
             p["b"].append(bf)
         wf, bf = fold_bn(self.fusion_layer[0].weight, self.fusion_layer[1])
         p["fw"], p["fb"] = ops.pack_weight(wf.reshape(wf.shape[0], -1), precise), bf
+        if not precise and len(set(self.in_channels_list)) == 1:   # all taps alike: one grouped conv launch
+            p["w_all"] = torch.cat(p["w"], 0).contiguous()
+            p["b_all"] = torch.cat(p["b"], 0).contiguous()
         self._packed = p
         return p
 
@@ -752,7 +757,16 @@ class ViTFeatureFusionNeck(nn.Module):
         ic = self.inter_channels
         tot = ic * self.num_inputs
         cat = torch.empty(M, tot * s, dtype=torch.bfloat16, device=tokens_list[0].device)
-        for i, t in enumerate(tokens_list):
+        stacked = _as_stacked(tokens_list)
+        C_in = self.in_channels_list[0]
+        grouped = ("w_all" in pk and stacked is not None and ic in (64, 128, 256) and (gh * gw) % 128 == 0
+                   and (128 % gw == 0 or gw % 128 == 0) and C_in % 64 == 0)
+        if grouped:
+            a = stacked[0, :, row0:, :]
+            a2 = a.as_strided((M, a.shape[2]), (a.stride(1), 1), a.storage_offset())
+            ops.gemm(a2, pk["w_all"], K=9 * C_in, bias=pk["b_all"], act="relu", out_bf16=cat, M=M, block_n=ic,
+                     conv=dict(C=C_in, gw=gw, gh=gh, B=B, a_bs=stacked.stride(1), G=self.num_inputs, a_gs=stacked.stride(0)))
+        for i, t in enumerate(tokens_list if not grouped else []):
             dst = cat[:, i * ic:]  # column slice; the lo half (fp32 mode) lands `tot` columns further right
             if precise:
                 _gemm_split_out_at(t, row0, gh, gw, self.in_channels_list[i], pk["w"][i], pk["b"][i], dst, tot)
@@ -776,6 +790,23 @@ class ViTFeatureFusionNeck(nn.Module):
             toks.append(ops.split_bf16(tf.view(-1, tf.shape[2])).view(B, gh * gw, -1) if precise else tb)
         fused, _ = self.forward_tokens(toks, 0, gh, gw)
         return [ops.tap_nchw(_with_dummy_cls(fused.view(B, gh * gw, -1)), gh, gw)]
+
+
+def _as_stacked(tokens_list):
+    """If the per-tap tensors are equally spaced views of one buffer, return it as [G, B, rows, C] (no copy), else None."""
+    t0 = tokens_list[0]
+    if len(tokens_list) < 2 or not all(t.shape == t0.shape and t.stride() == t0.stride() and t.dtype == t0.dtype for t in tokens_list):
+        return None
+    try:
+        base = t0.untyped_storage().data_ptr()
+        if any(t.untyped_storage().data_ptr() != base for t in tokens_list):
+            return None
+    except Exception:
+        return None
+    step = tokens_list[1].storage_offset() - t0.storage_offset()
+    if step <= 0 or any(t.storage_offset() != t0.storage_offset() + i * step for i, t in enumerate(tokens_list)):
+        return None
+    return t0.as_strided((len(tokens_list),) + tuple(t0.shape), (step,) + tuple(t0.stride()), t0.storage_offset())
 
 
 def _with_dummy_cls(tok: torch.Tensor) -> torch.Tensor:

@@ -102,6 +102,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, K: int | None = None, split_in: bo
     if conv is not None:  # implicit 3x3 conv: a is token-major [B, rows, ld], conv = dict(C, gh, gw, row0)
         g.conv_C, g.conv_gw, g.conv_gh, g.conv_B = conv["C"], conv["gw"], conv["gh"], conv["B"]
         g.a_bs = conv["a_bs"]
+        g.conv_G, g.a_gs = conv.get("G", 0), conv.get("a_gs", 0)
     _call(a, _lib.lib().dclip_gemm, C.byref(g), _stream(a))
     return out_f32, out_bf16
 

@@ -70,6 +70,10 @@ typedef struct {
    * gw | 128 or 128 | gw; otherwise use dclip_conv3x3_gather + a plain GEMM. */
   int conv_C, conv_gw, conv_gh, conv_B;
   long long a_bs;
+  /* grouped conv (conv_G > 1): G activation tensors (element stride a_gs) convolved with G filter banks of block_n
+   * outputs each; W is [G*block_n, 9*C], output column g*block_n + n.  One launch for the neck's 12 taps. */
+  int conv_G;
+  long long a_gs;
 } dclip_gemm_args;
 
 int dclip_gemm(dclip_handle_t h, const dclip_gemm_args* a, void* stream);
