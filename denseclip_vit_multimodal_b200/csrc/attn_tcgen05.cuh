@@ -31,6 +31,7 @@ struct AttnParams {
   __nv_bfloat16* out;          // out[b][row][h*64 + d]
   long long out_batch_stride;  // elements
   int ldo;                     // elements
+  int token_mode;              // 0: no MUFU token, 1: hand over after the exp phase, 2: hand over at 3/4 of it
   long long* dbg;              // optional timeline buffer (selftest only): clock64 stamps of CTA `dbg_cta`
   int dbg_cta;
 };
@@ -82,11 +83,34 @@ __device__ __forceinline__ void setmaxnreg_dec() {
 
 // One KV tile of the online softmax for one query row (= one thread): S (NC columns, fp32, TMEM) -> P (bf16, smem).
 // NC = 128 for regular tiles, 32 for a short ragged tail.  `valid` < NC masks the trailing columns.
-template <int NC, bool PT>
+// exp2 of two values on the FMA / ALU pipes (no MUFU): Cody-Waite split t = n + f with the 1.5*2^23 rounding constant,
+// degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max rel. error 1.0e-4, 38x below bf16 rounding), exponent
+// re-inserted with one integer multiply-add.  Offloads a fraction of the softmax exponentials from the SFU, which
+// is the bottleneck of head_dim-64 attention (profiles/r01_attention_notes.md).
+__device__ __forceinline__ void exp2_poly_x2(uint64_t t2, float& p0, float& p1) {
+  float ta, tb;
+  unpack_f32x2(t2, ta, tb);
+  t2 = pack_f32x2(fmaxf(ta, -126.f), fmaxf(tb, -126.f));
+  const uint64_t magic = pack_f32x2(12582912.f, 12582912.f);
+  const uint64_t r2 = add_f32x2(t2, magic);                                        // low mantissa bits = round(t)
+  const uint64_t n2 = add_f32x2(r2, pack_f32x2(-12582912.f, -12582912.f));         // round(t) as float
+  const uint64_t f2 = fma_f32x2(n2, pack_f32x2(-1.f, -1.f), t2);                   // t - round(t)
+  uint64_t q2 = fma_f32x2(pack_f32x2(0.05592203512787819f, 0.05592203512787819f), f2, pack_f32x2(0.24264007806777954f, 0.24264007806777954f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(0.6931210160255432f, 0.6931210160255432f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(0.9999244809150696f, 0.9999244809150696f));
+  float qa, qb, ra, rb;
+  unpack_f32x2(q2, qa, qb);
+  unpack_f32x2(r2, ra, rb);
+  p0 = __uint_as_float(__float_as_uint(qa) + (__float_as_uint(ra) << 23));
+  p1 = __uint_as_float(__float_as_uint(qb) + (__float_as_uint(rb) << 23));
+}
+
+// POLY = number of column pairs (of the 4 pairs in every group of 8 columns) whose exp2 runs on the FMA pipe
+template <int NC, bool PT, int POLY>
 __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint32_t tP, uint8_t* sProw, int r, int lane, int valid,
                                                   bool first, float sc, float& m_used, float& l, uint64_t* s_free_bar,
                                                   uint64_t* o_done_bar, uint32_t o_done_parity, int wg, bool last_tile,
-                                                  long long* dbg) {
+                                                  int token_mode, long long* dbg) {
   uint32_t su[NC];
 #pragma unroll
   for (int c = 0; c < NC / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, reinterpret_cast<uint32_t(&)[32]>(su[c * 32]));
@@ -140,7 +164,7 @@ __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint
   DCLIP_TL(if (dbg) dbg[4] = clock64();)
   // MUFU token: only one warpgroup at a time runs its exponential phase (the SFU pipe is the bottleneck at head_dim 64:
   // 128 ex2 per row per tile); the other one overlaps its TMEM loads / max / barrier work with it.
-  named_bar_sync(1 + wg, 256);
+  if (token_mode) named_bar_sync(1 + wg, 256);
   // P = exp2(S * sc - m * sc) -> bf16 -> swizzled smem (A operand of the PV MMA), 8 columns (16 B) at a time
   const uint64_t sc2 = pack_f32x2(sc, sc);
   const float nmc = -m_used * sc;
@@ -153,10 +177,14 @@ __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint
 #pragma unroll
     for (int e = 0; e < 8; e += 2) {
       const uint64_t t = fma_f32x2(pack_f32x2(__uint_as_float(su[c16 * 8 + e]), __uint_as_float(su[c16 * 8 + e + 1])), sc2, nmc2);
-      float t0, t1;
-      unpack_f32x2(t, t0, t1);
-      pv[e] = ex2_approx(t0);
-      pv[e + 1] = ex2_approx(t1);
+      if (e >= 8 - 2 * POLY) {
+        exp2_poly_x2(t, pv[e], pv[e + 1]);
+      } else {
+        float t0, t1;
+        unpack_f32x2(t, t0, t1);
+        pv[e] = ex2_approx(t0);
+        pv[e + 1] = ex2_approx(t1);
+      }
     }
     acc0 = add_f32x2(acc0, add_f32x2(pack_f32x2(pv[0], pv[1]), pack_f32x2(pv[2], pv[3])));
     acc1 = add_f32x2(acc1, add_f32x2(pack_f32x2(pv[4], pv[5]), pack_f32x2(pv[6], pv[7])));
@@ -171,8 +199,10 @@ __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint
       *reinterpret_cast<uint4*>(sProw + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4)) =
           make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
     }
+    // token_mode 2: early hand-over once 3/4 of this tile's exponentials are issued
+    if (token_mode == 2 && c16 == (3 * NC / 32) && (!last_tile || wg == 0)) named_bar_arrive(2 - wg, 256);
   }
-  if (!last_tile || wg == 0) named_bar_arrive(2 - wg, 256);  // hand the token over (WG1 skips its final, unmatched arrive)
+  if (token_mode == 1 && (!last_tile || wg == 0)) named_bar_arrive(2 - wg, 256);  // hand the token over (WG1 skips its final, unmatched arrive)
   float a0, a1, a2, a3;
   unpack_f32x2(acc0, a0, a1);
   unpack_f32x2(acc1, a2, a3);
@@ -180,7 +210,7 @@ __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint
   DCLIP_TL(if (dbg) dbg[3] = clock64();)
 }
 
-template <bool PT>
+template <bool PT, int POLY = 0>
 __global__ void __launch_bounds__(AttnCfgT<PT>::THREADS, 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -360,7 +390,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t tP = tmem_base + 384 + i * 64 + lane_off;
     const float sc = p.scale_log2;
     float m_used = -INFINITY, l = 0.f;
-    if (i == 1) named_bar_arrive(1, 256);  // WG0 owns the MUFU token first
+    if (i == 1 && p.token_mode) named_bar_arrive(1, 256);  // WG0 owns the MUFU token first
 
     for (int j = 0; j < T; ++j) {
       DCLIP_TL(if (p.dbg && blockIdx.x == p.dbg_cta && (warp & 3) == 0 && lane == 0) p.dbg[(i * 32 + j) * 8 + 6] = clock64();)
@@ -371,9 +401,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       DCLIP_TL(dbg = (p.dbg && blockIdx.x == p.dbg_cta && (warp & 3) == 0 && lane == 0) ? p.dbg + (i * 32 + j) * 8 : nullptr;)
       DCLIP_TL(if (dbg) dbg[0] = clock64();)
       if (valid > 32)
-        attn_softmax_tile<128, PT>(tS, tO, tP, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, dbg);
+        attn_softmax_tile<128, PT, POLY>(tS, tO, tP, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
       else
-        attn_softmax_tile<32, PT>(tS, tO, tP, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, dbg);
+        attn_softmax_tile<32, PT, POLY>(tS, tO, tP, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
       if constexpr (PT) tmem_wait_st(); else fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();

@@ -288,6 +288,8 @@ inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
   DCLIP_REQUIRE(p.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && p.out_batch_stride % 8 == 0, "attention out alignment");
   AttnPlan plan;
   plan.p = p;
+  static const int token_env = [] { const char* e = getenv("DCLIP_ATTN_TOKEN"); return e ? atoi(e) : 1; }();
+  plan.p.token_mode = token_env;
   plan.tmQ = make_tmap_tokens_bf16(op.q, p.B, op.Nq_total, op.ldq, op.q_bs);
   plan.tmK = make_tmap_tokens_bf16(op.k, p.B, p.Nk, op.ldk, op.k_bs);
   plan.tmV = make_tmap_tokens_bf16(op.v, p.B, p.Nk, op.ldv, op.v_bs);
@@ -296,23 +298,32 @@ inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
   return plan;
 }
 
-template <bool PT>
+template <bool PT, int POLY>
 inline void run_attn_variant(const AttnPlan& plan, cudaStream_t stream) {
   using Cfg = AttnCfgT<PT>;
   static bool attr_set = false;
   if (!attr_set) {
-    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<PT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  attn_fwd_tcgen05_kernel<PT><<<plan.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.p);
+  attn_fwd_tcgen05_kernel<PT, POLY><<<plan.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.p);
   DCLIP_CHECK_CUDA(cudaGetLastError());
 }
 
-// P in TMEM (TS MMA) is the production variant; the shared-memory P variant is kept for A/B checks (DCLIP_ATTN_P_SMEM=1)
+// Production variant: P in TMEM (TS MMA) + DCLIP_ATTN_POLY_DEFAULT of every 4 exp2 pairs on the FMA pipe.
+// A/B knobs (selftests only): DCLIP_ATTN_P_SMEM=1 (P through shared memory), DCLIP_ATTN_POLY=0|1|2.
+#ifndef DCLIP_ATTN_POLY_DEFAULT
+#define DCLIP_ATTN_POLY_DEFAULT 0
+#endif
 inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
   static const bool p_smem = [] { const char* e = getenv("DCLIP_ATTN_P_SMEM"); return e && e[0] == '1'; }();
-  if (p_smem) run_attn_variant<false>(plan, stream);
-  else run_attn_variant<true>(plan, stream);
+  static const int poly = [] { const char* e = getenv("DCLIP_ATTN_POLY"); return e ? atoi(e) : DCLIP_ATTN_POLY_DEFAULT; }();
+  if (p_smem) return run_attn_variant<false, 0>(plan, stream);
+  switch (poly) {
+    case 0: return run_attn_variant<true, 0>(plan, stream);
+    case 2: return run_attn_variant<true, 2>(plan, stream);
+    default: return run_attn_variant<true, 1>(plan, stream);
+  }
 }
 
 template <int QB>

@@ -48,3 +48,25 @@ def test_forward_matches_reference_golden(golden_cases, name, precision):
             assert e <= 5e-2, (k, e)
     # forward() also stashes what the reference computes and drops
     assert rel_err(model.last_score_map, score) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_patch14_ragged_grid_against_oracle(precision):
+    """ViT-L/14-style geometry in miniature: patch 14 (K = 588, padded to 592 for TMA), trailing pixels dropped, a 3x5
+    grid that cannot be tiled by 128 pixels (gather-conv fallback), last-layer-only tap, 'backbone' context feature."""
+    import denseclip_vit_multimodal_b200 as D
+    cfg = O.model_config("tiny", 2)
+    cfg["backbone"].update(patch_size=14, input_resolution=28, out_indices=[1])
+    cfg["context_feature"] = "backbone"
+    model = D.DenseCLIP(**copy.deepcopy(cfg), precision=precision)
+    sd = O.seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 21)
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().cuda()
+    img = O.synthetic_images(2, 50, 76, seed=9)      # 50x76 -> 3x5 patches of 14, 8 / 6 trailing pixels dropped
+    with torch.no_grad():
+        out = model(img.cuda(), return_loss=False)
+        ref = O.denseclip_forward(sd, cfg, img, return_intermediates=True)
+    tol = 1e-3 if precision == "fp32" else 5e-2
+    assert out["seg"].shape == (2, 19, 50, 76)
+    assert rel_err(out["seg"], ref["seg"]) <= tol and rel_err(out["depth"], ref["depth"]) <= tol
+    assert float((model.last_score_map.cpu() - ref["score"]).abs().max()) <= (1e-4 if precision == "fp32" else 2e-2)

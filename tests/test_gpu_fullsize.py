@@ -74,3 +74,17 @@ def test_cuda_graph_replay_matches_eager(models):
             assert torch.equal(pm["seg"].long(), eager[0].argmax(1))
         finally:
             m.enable_cuda_graph(False)
+
+
+def test_pipelined_predictor_matches_direct_predict(models):
+    from denseclip_vit_multimodal_b200.pipeline import PipelinedPredictor
+    m, _ = models
+    g = torch.Generator().manual_seed(4)
+    hosts = [torch.randn(2, 3, 512, 1024, generator=g).pin_memory() for _ in range(5)]
+    with torch.no_grad():
+        direct = [{k: v.clone().cpu() for k, v in m.predict(h.cuda()).items()} for h in hosts]
+        pipe = PipelinedPredictor(m, (2, 3, 512, 1024), "cuda")
+        got = [{k: v.clone() for k, v in r.items()} for r in pipe.run(hosts)]
+    assert len(got) == len(hosts)
+    for d, r in zip(direct, got):
+        assert torch.equal(d["seg"], r["seg"]) and torch.equal(d["depth"], r["depth"])
