@@ -344,22 +344,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       float4 rr[8];
       load_resid(half, rr);
+      float4 bias_t[(BN / 64 + 1) / 2 * 2];
+#pragma unroll
+      for (int ci = 0; ci < (BN / 64 + 1) / 2 * 2; ++ci) {
+        const int cc = n_blk * BN + (half + 2 * ci) * 32 + 4 * cq;
+        bias_t[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && half + 2 * ci < BN / 32 && cc < p.N) bias_t[ci] = *reinterpret_cast<const float4*>(p.bias + cc);
+      }
       DCLIP_GTL(if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 16) p.dbg[it * 8 + 0] = clock64();)
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       DCLIP_GTL(if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 16) p.dbg[it * 8 + 1] = clock64();)
-#pragma unroll 1
-      for (int chunk = half; chunk < BN / 32; chunk += 2) {
+      auto process = [&](int chunk, const float4 (&rres)[8], const float4 b4) {
         const int c = n_blk * BN + chunk * 32 + 4 * cq;
         const bool col_ok = c < p.N;  // N % 4 == 0 is required by the launcher
-        float4 rr_next[8];
-        load_resid(chunk + 2, rr_next);
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok) b4 = *reinterpret_cast<const float4*>(p.bias + c);
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + as * BN + chunk * 32 + (uint32_t(q * 32) << 16), r);
         tmem_wait_ld();
-        if (p.dbg_mode == 1) continue;
+        if (p.dbg_mode == 1) return;
         // row-per-lane -> staging (16B chunk j of row `lane` lands at physical chunk j ^ (lane & 7))
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -372,13 +374,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int i = 4 * k + sub;
             if (i < rows_valid) {
               float4 v = *reinterpret_cast<const float4*>(stg + i * 128 + ((cq ^ (i & 7)) << 4));
-              v.x = apply_act_t<ACT>(v.x + b4.x, p.act) * p.out_scale + rr[k].x;
-              v.y = apply_act_t<ACT>(v.y + b4.y, p.act) * p.out_scale + rr[k].y;
-              v.z = apply_act_t<ACT>(v.z + b4.z, p.act) * p.out_scale + rr[k].z;
-              v.w = apply_act_t<ACT>(v.w + b4.w, p.act) * p.out_scale + rr[k].w;
-              if (has_f32) {
-                *reinterpret_cast<float4*>(p.out_f32 + orow[k] * p.ldc + c) = v;
-              }
+              v.x = apply_act_t<ACT>(v.x + b4.x, p.act) * p.out_scale + rres[k].x;
+              v.y = apply_act_t<ACT>(v.y + b4.y, p.act) * p.out_scale + rres[k].y;
+              v.z = apply_act_t<ACT>(v.z + b4.z, p.act) * p.out_scale + rres[k].z;
+              v.w = apply_act_t<ACT>(v.w + b4.w, p.act) * p.out_scale + rres[k].w;
+              if (has_f32) *reinterpret_cast<float4*>(p.out_f32 + orow[k] * p.ldc + c) = v;
               if (has_b16) {
                 const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
                 *reinterpret_cast<uint2*>(p.out_bf16 + orow[k] * p.ldcb + c) = make_uint2(h0, h1);
@@ -392,8 +392,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
         __syncwarp();
+      };
+      // ping-pong residual buffers (no register copies: a copy would wait for the loads it is meant to hide); the
+      // per-column bias of all this warp's chunks was loaded before the accumulator wait as well
 #pragma unroll
-        for (int k = 0; k < 8; ++k) rr[k] = rr_next[k];
+      for (int ci = 0; ci < (BN / 64 + 1) / 2; ++ci) {
+        const int chunk = half + 4 * ci;
+        if (chunk < BN / 32) {
+          float4 rr2[8];
+          load_resid(chunk + 2, rr2);
+          process(chunk, rr, bias_t[2 * ci]);
+          if (chunk + 2 < BN / 32) {
+            load_resid(chunk + 4, rr);
+            process(chunk + 2, rr2, bias_t[2 * ci + 1]);
+          }
+        }
         DCLIP_GTL(if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 16 && chunk < 8) p.dbg[it * 8 + 2 + chunk / 2] = clock64();)
       }
       tc_fence_before();
