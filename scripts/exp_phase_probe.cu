@@ -1,0 +1,89 @@
+// Stand-alone timing of the flash-attention exponential phase (the straight-line code of attn_tcgen05.cuh: 128 or 64
+// scores per thread in registers -> FFMA2, MUFU.EX2, row-sum FADD2, bf16 pack), with 1, 2 or 4 warps per SM
+// sub-partition and no other activity on the SM.  Answers: is ~11.3 cycles per MUFU a property of the compiled
+// instruction stream, or of interference inside the attention kernel?
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I denseclip_vit_multimodal_b200/csrc -o /tmp/exp_probe scripts/exp_phase_probe.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "ptx.cuh"
+using namespace dclip;
+
+template <int NC>
+__global__ void __launch_bounds__(512, 1) probe(const float* in, uint32_t* out, long long* cyc, int iters, float sc) {
+  uint32_t su[NC];
+  const float* src = in + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * NC;
+#pragma unroll
+  for (int e = 0; e < NC; ++e) su[e] = __float_as_uint(src[e]);
+  float l = 0.f, m_used = 1.0f;
+  uint32_t sink = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    const uint64_t sc2 = pack_f32x2(sc, sc);
+    const float nmc = -m_used * sc;
+    const uint64_t nmc2 = pack_f32x2(nmc, nmc);
+    uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
+    uint32_t pk[16];
+#pragma unroll
+    for (int g = 0; g < NC / 8; ++g) {
+      float pv[8];
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        float a, b;
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(su[g * 8 + e]), __uint_as_float(su[g * 8 + e + 1])), sc2, nmc2), a, b);
+        pv[e] = ex2_approx(a);
+        pv[e + 1] = ex2_approx(b);
+      }
+      acc0 = add_f32x2(acc0, add_f32x2(pack_f32x2(pv[0], pv[1]), pack_f32x2(pv[2], pv[3])));
+      acc1 = add_f32x2(acc1, add_f32x2(pack_f32x2(pv[4], pv[5]), pack_f32x2(pv[6], pv[7])));
+      pk[(g & 3) * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
+      pk[(g & 3) * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+      pk[(g & 3) * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
+      pk[(g & 3) * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
+      if ((g & 3) == 3) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sink ^= pk[k];  // stands in for the tcgen05.st of 32 columns of P
+      }
+    }
+    float a0, a1, a2, a3;
+    unpack_f32x2(acc0, a0, a1);
+    unpack_f32x2(acc1, a2, a3);
+    l += (a0 + a1) + (a2 + a3);
+    m_used += 1e-6f * l;  // loop-carried so iterations cannot be merged
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sink + __float_as_uint(l);
+  if ((threadIdx.x & 31) == 0) cyc[blockIdx.x * 16 + (threadIdx.x >> 5)] = t1 - t0;
+}
+
+template <int NC>
+void run(int warps) {
+  const int threads = warps * 32, iters = 2000;
+  float* in; uint32_t* out; long long* cyc;
+  cudaMalloc(&in, (size_t)148 * 512 * NC * 4);
+  cudaMemset(in, 0, (size_t)148 * 512 * NC * 4);
+  cudaMalloc(&out, 148 * 512 * 4);
+  cudaMalloc(&cyc, 148 * 16 * 8);
+  probe<NC><<<148, threads>>>(in, out, cyc, iters, 0.18f);
+  probe<NC><<<148, threads>>>(in, out, cyc, iters, 0.18f);
+  cudaDeviceSynchronize();
+  long long h[16];
+  cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+  const double per_tile = (double)h[0] / iters;
+  const double mufu_per_smsp = (double)NC * (warps / 4.0);  // MUFU warp-instructions per sub-partition per iteration
+  printf("NC=%3d  %d warp(s)/sub-partition: %7.1f cycles per tile-row pass  -> %5.2f cycles per MUFU instr per sub-partition\n", NC,
+         warps / 4, per_tile, per_tile / mufu_per_smsp);
+  cudaFree(in); cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+  run<128>(4); run<128>(8);
+  run<64>(4); run<64>(8); run<64>(16);
+  cudaError_t e = cudaDeviceSynchronize();
+  printf("%s\n", cudaGetErrorString(e));
+  return e != cudaSuccess;
+}
