@@ -11,8 +11,8 @@
 #include "ptx.cuh"
 using namespace dclip;
 
-template <int NC>
-__global__ void __launch_bounds__(512, 1) probe(const float* in, uint32_t* out, long long* cyc, int iters, float sc) {
+template <int NC, int VARIANT>
+__global__ void __launch_bounds__(256, 1) probe(const float* in, uint32_t* out, long long* cyc, int iters, float sc, int z) {
   uint32_t su[NC];
   const float* src = in + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * NC;
 #pragma unroll
@@ -27,27 +27,69 @@ __global__ void __launch_bounds__(512, 1) probe(const float* in, uint32_t* out, 
     const float nmc = -m_used * sc;
     const uint64_t nmc2 = pack_f32x2(nmc, nmc);
     uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
-    uint32_t pk[16];
+    if constexpr (VARIANT == 0) {
+      uint32_t pk[16];
 #pragma unroll
-    for (int g = 0; g < NC / 8; ++g) {
-      float pv[8];
+      for (int g = 0; g < NC / 8; ++g) {
+        float pv[8];
 #pragma unroll
-      for (int e = 0; e < 8; e += 2) {
-        float a, b;
-        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(su[g * 8 + e]), __uint_as_float(su[g * 8 + e + 1])), sc2, nmc2), a, b);
-        pv[e] = ex2_approx(a);
-        pv[e + 1] = ex2_approx(b);
+        for (int e = 0; e < 8; e += 2) {
+          float a, b;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(su[g * 8 + e]), __uint_as_float(su[g * 8 + e + 1])), sc2, nmc2), a, b);
+          pv[e] = ex2_approx(a);
+          pv[e + 1] = ex2_approx(b);
+        }
+        acc0 = add_f32x2(acc0, add_f32x2(pack_f32x2(pv[0], pv[1]), pack_f32x2(pv[2], pv[3])));
+        acc1 = add_f32x2(acc1, add_f32x2(pack_f32x2(pv[4], pv[5]), pack_f32x2(pv[6], pv[7])));
+        pk[(g & 3) * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
+        pk[(g & 3) * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+        pk[(g & 3) * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
+        pk[(g & 3) * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
+        if ((g & 3) == 3) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) sink ^= pk[k];  // stands in for the tcgen05.st of 32 columns of P
+        }
       }
-      acc0 = add_f32x2(acc0, add_f32x2(pack_f32x2(pv[0], pv[1]), pack_f32x2(pv[2], pv[3])));
-      acc1 = add_f32x2(acc1, add_f32x2(pack_f32x2(pv[4], pv[5]), pack_f32x2(pv[6], pv[7])));
-      pk[(g & 3) * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
-      pk[(g & 3) * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
-      pk[(g & 3) * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
-      pk[(g & 3) * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
-      if ((g & 3) == 3) {
+    } else {
+      // results are written to a second register array (the real kernel overwrites su in place; here su must survive)
+      uint32_t ex[NC];
+      auto issue = [&](int c) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) sink ^= pk[k];  // stands in for the tcgen05.st of 32 columns of P
-      }
+        for (int e = c * 32; e < c * 32 + 32; e += 2) {
+          float a, b;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(su[e]), __uint_as_float(su[e + 1])), sc2, nmc2), a, b);
+          ex[e] = __float_as_uint(ex2_approx(a));
+          ex[e + 1] = __float_as_uint(ex2_approx(b));
+        }
+      };
+      auto consume = [&](int c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pv[k] = __uint_as_float(ex[c * 32 + g * 8 + k]);
+          acc0 = add_f32x2(acc0, add_f32x2(pack_f32x2(pv[0], pv[1]), pack_f32x2(pv[2], pv[3])));
+          acc1 = add_f32x2(acc1, add_f32x2(pack_f32x2(pv[4], pv[5]), pack_f32x2(pv[6], pv[7])));
+          pk[g * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
+          pk[g * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+          pk[g * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
+          pk[g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sink ^= pk[k];
+      };
+      static_assert(VARIANT == 0 || NC == 128, "pipelined variant: 4 chunks");
+#pragma unroll 1
+      for (int k = z; k < 1; ++k) issue(0);
+#pragma unroll 1
+      for (int k = z; k < 1; ++k) { issue(1); consume(0); }
+#pragma unroll 1
+      for (int k = z; k < 1; ++k) { issue(2); consume(1); }
+#pragma unroll 1
+      for (int k = z; k < 1; ++k) { issue(3); consume(2); }
+#pragma unroll 1
+      for (int k = z; k < 1; ++k) consume(3);
     }
     float a0, a1, a2, a3;
     unpack_f32x2(acc0, a0, a1);
@@ -60,29 +102,30 @@ __global__ void __launch_bounds__(512, 1) probe(const float* in, uint32_t* out, 
   if ((threadIdx.x & 31) == 0) cyc[blockIdx.x * 16 + (threadIdx.x >> 5)] = t1 - t0;
 }
 
-template <int NC>
+template <int NC, int VARIANT>
 void run(int warps) {
   const int threads = warps * 32, iters = 2000;
   float* in; uint32_t* out; long long* cyc;
-  cudaMalloc(&in, (size_t)148 * 512 * NC * 4);
-  cudaMemset(in, 0, (size_t)148 * 512 * NC * 4);
-  cudaMalloc(&out, 148 * 512 * 4);
+  cudaMalloc(&in, (size_t)148 * 256 * NC * 4);
+  cudaMemset(in, 0, (size_t)148 * 256 * NC * 4);
+  cudaMalloc(&out, 148 * 256 * 4);
   cudaMalloc(&cyc, 148 * 16 * 8);
-  probe<NC><<<148, threads>>>(in, out, cyc, iters, 0.18f);
-  probe<NC><<<148, threads>>>(in, out, cyc, iters, 0.18f);
+  probe<NC, VARIANT><<<148, threads>>>(in, out, cyc, iters, 0.18f, 0);
+  probe<NC, VARIANT><<<148, threads>>>(in, out, cyc, iters, 0.18f, 0);
   cudaDeviceSynchronize();
   long long h[16];
   cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
   const double per_tile = (double)h[0] / iters;
   const double mufu_per_smsp = (double)NC * (warps / 4.0);  // MUFU warp-instructions per sub-partition per iteration
-  printf("NC=%3d  %d warp(s)/sub-partition: %7.1f cycles per tile-row pass  -> %5.2f cycles per MUFU instr per sub-partition\n", NC,
+  printf("variant %d NC=%3d  %d warp(s)/sub-partition: %7.1f cycles per tile-row pass  -> %5.2f cycles per MUFU instr per sub-partition\n", VARIANT, NC,
          warps / 4, per_tile, per_tile / mufu_per_smsp);
   cudaFree(in); cudaFree(out); cudaFree(cyc);
 }
 
 int main() {
-  run<128>(4); run<128>(8);
-  run<64>(4); run<64>(8); run<64>(16);
+  run<128, 0>(4); run<128, 0>(8);
+  run<64, 0>(4); run<64, 0>(8);
+  run<128, 1>(4); run<128, 1>(8);
   cudaError_t e = cudaDeviceSynchronize();
   printf("%s\n", cudaGetErrorString(e));
   return e != cudaSuccess;
