@@ -266,7 +266,7 @@ int dclip_upsample_bilinear(dclip_handle_t h, const float* in, int in_nchw, long
     UpsampleParams p{in, in_nchw, ldi, in_bs, out, B, C, hh, ww, H, W};
     // token-major input whose rows hold (C rounded up to 4) readable floats: all-channel fast path
     if (!in_nchw && ldi % 4 == 0 && ldi >= ((C + 3) & ~3) && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && in_bs % 4 == 0) {
-      const long long total = (long long)B * H * (W / 4);
+      const long long total = (long long)B * ((H + UP_ROWS - 1) / UP_ROWS) * (W / 4);
       const int grid = int(std::min<long long>((total + 255) / 256, 148 * 64));
       upsample_bilinear_tok_kernel<<<std::max(grid, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     } else {
@@ -283,9 +283,24 @@ int dclip_upsample_argmax(dclip_handle_t h, const float* in, long long ldi, long
   return guarded(h, [&] {
     DCLIP_REQUIRE(W % 4 == 0 && K > 0 && K <= 256, "upsample_argmax: W %% 4 == 0 and K <= 256 required");
     UpsampleArgmaxParams p{in, ldi, in_bs, out, B, K, hh, ww, H, W};
-    const long long total = (long long)B * H * (W / 4);
-    const int grid = int(std::min<long long>((total + 255) / 256, 148 * 32));
-    upsample_argmax_kernel<<<std::max(grid, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int k4 = (K + 3) / 4;
+    if (k4 <= 5 && ldi % 4 == 0 && ldi >= 4 * k4 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && in_bs % 4 == 0) {
+      // class scores cached in registers per thread strip (the 19-class Cityscapes head: K4 = 5)
+      const long long total = (long long)B * ((H + UP_ROWS - 1) / UP_ROWS) * (W / 4);
+      const int grid = std::max(int(std::min<long long>((total + 255) / 256, 148 * 64)), 1);
+      switch (k4) {
+        case 1: upsample_argmax_strip_kernel<1><<<grid, 256, 0, st>>>(p); break;
+        case 2: upsample_argmax_strip_kernel<2><<<grid, 256, 0, st>>>(p); break;
+        case 3: upsample_argmax_strip_kernel<3><<<grid, 256, 0, st>>>(p); break;
+        case 4: upsample_argmax_strip_kernel<4><<<grid, 256, 0, st>>>(p); break;
+        default: upsample_argmax_strip_kernel<5><<<grid, 256, 0, st>>>(p); break;
+      }
+    } else {
+      const long long total = (long long)B * H * (W / 4);
+      const int grid = int(std::min<long long>((total + 255) / 256, 148 * 32));
+      upsample_argmax_kernel<<<std::max(grid, 1), 256, 0, st>>>(p);
+    }
     check_launch(h);
   });
 }

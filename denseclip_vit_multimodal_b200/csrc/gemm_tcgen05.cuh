@@ -72,7 +72,7 @@ struct GemmCfg {
   static constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 256;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = BN == 192 ? 512 : 2 * BN;  // tcgen05.alloc wants a power of two; the two accumulators sit at 0 and BN
   static constexpr int THREADS = 128 + EPI_WARPS * 32;
 };
 

@@ -156,6 +156,16 @@ inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
   const GemmParams& p = plan.p;
   const int flags = (p.residual ? EPI_RESID : 0) | (p.out_f32 ? EPI_OUT_F32 : 0) | (p.out_bf16 ? EPI_OUT_BF16 : 0) |
                     (p.split_out ? EPI_SPLIT : 0) | (p.remap_P > 0 ? EPI_REMAP : 0);
+  // BLOCK_N 192 exists only as CTA-pair instantiations of the fp32-residual epilogues (N = 768: 7 full waves of
+  // 256x192 pair tiles instead of 5.2 -> 6 waves of 256x256)
+  if constexpr (BN == 192) {
+    DCLIP_REQUIRE(p.cluster == 2, "BLOCK_N 192 is a CTA-pair configuration");
+    if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32))
+      return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32, true>(plan, stream);
+    if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32 | EPI_OUT_BF16))
+      return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32 | EPI_OUT_BF16, true>(plan, stream);
+    return launch_gemm_inst<BN, -1, -1, true>(plan, stream);
+  } else {
   // CTA-pair (cta_group::2) instantiations exist for the 256-wide tile and the hot ViT-block epilogues
   if constexpr (BN == 256) {
     if (p.cluster == 2) {
@@ -184,6 +194,7 @@ inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
     return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32 | EPI_OUT_BF16>(plan, stream);
   if (p.act == ACT_RELU && flags == EPI_OUT_BF16) return launch_gemm_inst<BN, ACT_RELU, EPI_OUT_BF16>(plan, stream);
   return launch_gemm_inst<BN, -1, -1>(plan, stream);
+  }
 }
 
 // bn = 0: choose automatically.
@@ -195,8 +206,23 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
   if (p.out_bf16) DCLIP_REQUIRE(p.ldcb % 4 == 0 && p.split_out_off % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 7) == 0, "out_bf16 alignment");
   if (p.residual) DCLIP_REQUIRE(p.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0, "residual alignment");
   if (p.bias) DCLIP_REQUIRE((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "bias alignment");
-  if (bn == 0) bn = p.N > 128 ? 256 : (p.N > 64 ? 128 : 64);
-  DCLIP_REQUIRE(bn == 256 || bn == 128 || bn == 64, "unsupported BLOCK_N %d", bn);
+  static const int cluster_env = [] { const char* e = getenv("DCLIP_GEMM_CLUSTER"); return e ? atoi(e) : -1; }();
+  const int num_m_pairs = ((p.M + 127) / 128 + 1) / 2;
+  if (bn == 0) {
+    bn = p.N > 128 ? 256 : (p.N > 64 ? 128 : 64);
+    // wave quantisation of the CTA-pair grid: N = 768 with M = 32784 is 387 pair tiles of 256x256 on 74 pairs (6 waves, 87%
+    // full) but 516 tiles of 256x192 (7 waves, 99.6% full).  Only the fp32-residual epilogues are instantiated at 192, and
+    // only short-K GEMMs win (measured, B200: K = 768 0.062 -> 0.054 ms; K = 3072 0.136 -> 0.140 ms, the narrower tile
+    // costs more operand traffic per MMA than the fuller last wave saves).
+    static const bool no192 = [] { const char* e = getenv("DCLIP_GEMM_NO_BN192"); return e && e[0] == '1'; }();
+    if (bn == 256 && !no192 && cluster_env != 0 && p.K <= 1536 && p.N % 192 == 0 && p.conv_C == 0 && p.residual && p.out_f32 && !p.split_out && p.remap_P == 0) {
+      const int pairs = sm_count() / 2;
+      const long long u256 = (long long)num_m_pairs * ((p.N + 255) / 256), u192 = (long long)num_m_pairs * (p.N / 192);
+      const long long c256 = (u256 + pairs - 1) / pairs * 256, c192 = (u192 + pairs - 1) / pairs * 192;
+      if (u192 >= sm_count() && c192 * 100 < c256 * 95) bn = 192;
+    }
+  }
+  DCLIP_REQUIRE(bn == 256 || bn == 192 || bn == 128 || bn == 64, "unsupported BLOCK_N %d", bn);
   GemmPlan plan;
   plan.p = p;
   plan.bn = bn;
@@ -216,16 +242,19 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
     plan.tmA = make_tmap_2d_bf16(op.A, p.M, kcols, op.lda, 128);
   }
   // CTA-pair mode (cta_group::2, 256 x 256 tile per pair, each CTA stages half of W): when there are enough pair-units
-  static const int cluster_env = [] { const char* e = getenv("DCLIP_GEMM_CLUSTER"); return e ? atoi(e) : -1; }();
   const int num_m_blocks = (p.M + 127) / 128;
   bool use_cluster = bn == 256 && p.conv_C == 0 && ((num_m_blocks + 1) / 2) * ((p.N + bn - 1) / bn) >= sm_count();
   if (cluster_env == 0) use_cluster = false;
   if (cluster_env == 2 && bn == 256 && p.conv_C == 0) use_cluster = true;
+  if (bn == 192) {
+    DCLIP_REQUIRE(p.conv_C == 0, "BLOCK_N 192: plain GEMM only");
+    use_cluster = true;
+  }
   plan.p.cluster = use_cluster ? 2 : 1;
   plan.tmB = make_tmap_2d_bf16(op.W, p.N, kcols, op.ldw, use_cluster ? bn / 2 : bn);
   memset(&plan.tmC, 0, sizeof(plan.tmC));
   static const bool no_tma_store = [] { const char* e = getenv("DCLIP_GEMM_NO_TMA_STORE"); return e && e[0] == '1'; }();
-  if (!no_tma_store && p.out_bf16 && !p.out_f32 && !p.residual && !p.split_out && p.remap_P == 0 && p.ldcb % 8 == 0 &&
+  if (!no_tma_store && bn != 192 && p.out_bf16 && !p.out_f32 && !p.residual && !p.split_out && p.remap_P == 0 && p.ldcb % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0 && (p.dbg_mode == 0 || p.dbg_mode == 5)) {
     uint64_t dims[2] = {uint64_t(p.N), uint64_t(p.M)};
     uint64_t str[1] = {uint64_t(p.ldcb) * 2};
@@ -249,6 +278,7 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
 inline void run_gemm(const GemmPlan& plan, cudaStream_t stream) {
   switch (plan.bn) {
     case 256: launch_gemm_bn<256>(plan, stream); break;
+    case 192: launch_gemm_bn<192>(plan, stream); break;
     case 128: launch_gemm_bn<128>(plan, stream); break;
     case 64: launch_gemm_bn<64>(plan, stream); break;
     default: throw Error{"unsupported BLOCK_N"};

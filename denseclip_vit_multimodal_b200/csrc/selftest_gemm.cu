@@ -297,6 +297,9 @@ int main(int argc, char** argv) {
   run_case(1000, 768, 768, 256, 3, false);
   run_case(777, 512, 320, 256, 4, false);
   run_case(20000, 512, 256, 256, 2, false);  // many tiles per CTA: exercises ring + accumulator phases
+  run_case(1000, 768, 768, 192, 2, false);   // CTA-pair 256x192 tiles (fp32-residual epilogue)
+  run_case(20000, 384, 256, 192, 2, false);
+  run_case(777, 576, 320, 192, 4, false);
   run_split_case(200, 256, 256);
   if (!quick) {
     const int M = 16 * 2049;
@@ -304,9 +307,11 @@ int main(int argc, char** argv) {
     run_case(M, 2304, 768, 128, 0, true);
     run_case(M, 768, 768, 256, 2, true);
     run_case(M, 768, 768, 128, 2, true);
+    run_case(M, 768, 768, 192, 2, true);
     run_case(M, 3072, 768, 256, 1, true);
     run_case(M, 768, 3072, 256, 2, true);
     run_case(M, 768, 3072, 128, 2, true);
+    run_case(M, 768, 3072, 192, 2, true);
   }
   printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST PASSED\n", g_fail);
   return g_fail ? 1 : 0;

@@ -122,6 +122,25 @@ def test_layout_mean_score_upsample(ops):
     assert rel_err(ops.upsample_bilinear(ref_nchw, (13 * 4, 20)), F.interpolate(ref_nchw, size=(52, 20), mode="bilinear", align_corners=False)) < 1e-6
 
 
+@pytest.mark.parametrize("K,ld", [(1, 4), (5, 8), (19, 20), (19, 24), (21, 24)])   # K4 = 1, 2, 5, 5 + padding, generic fallback
+@pytest.mark.parametrize("hw,HW", [((5, 7), (37, 52)), ((3, 4), (48, 64)), ((9, 6), (9, 8))])   # ragged ratio / x16 / ~identity
+def test_upsample_strips_ragged(ops, K, ld, hw, HW):
+    """The strip kernels (4 px x 16 rows per thread, source rows cached while (y0, y1) is unchanged) against
+    F.interpolate for sizes that are not a multiple of the strip height and scales that are not integers."""
+    (h, w), (H, W) = hw, HW
+    B = 2
+    low = _rand(B, h * w, ld, seed=31 + K)
+    ref = F.interpolate(low[..., :K].permute(0, 2, 1).reshape(B, K, h, w), size=(H, W), mode="bilinear", align_corners=False)
+    up = ops.upsample_bilinear(low, (H, W), tokens_hw=(h, w), channels=K)
+    assert up.shape == ref.shape and rel_err(up, ref) < 1e-6
+    am = ops.upsample_argmax(low, (H, W), tokens_hw=(h, w), channels=K).long()
+    # ties / last-bit differences: accept a different class only where the two top scores are within fp32 rounding
+    bad = am != ref.argmax(1)
+    if bad.any():
+        top2 = ref.topk(2, dim=1).values if K > 1 else None
+        assert K > 1 and float((top2[:, 0] - top2[:, 1])[bad].abs().max()) < 1e-6
+
+
 @pytest.mark.parametrize("gh,gw", [(8, 16), (4, 8), (2, 64)])   # implicit-conv TMA path / gather fallback / one-row box
 def test_conv3x3_implicit_gemm(ops, gh, gw):
     from denseclip_vit_multimodal_b200 import models as M
