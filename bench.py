@@ -31,7 +31,7 @@ ENCODER_FLOPS_PER_IMAGE = 505.25e9          # patch 2.416 + QKV 87.
 ATTN_FLOPS_PER_IMAGE_LAYER = 154.770e9 / 12  # QK^T + PV, 12 heads x 2049^2 x 64 x 2 x 2
 # measured on this pool's B200s by the driver (MEASURED_PEAKS.json at the time of writing); re-read from the file if present
 RECORDED_PEAKS = {"hbm_gbs": 6541.8, "bf16_tflops": 1674.0, "bf16_tflops_sustained": 1403.8}
-ATTN_DRAM_TRAFFIC_BYTES = 185.2e6           # profiles/r01_attn_ncu.txt: dram read 151.1 MB + write 34.1 MB per launch (B=16)
+ATTN_DRAM_TRAFFIC_BYTES = 183.0e6           # profiles/r01_attn_ncu_final.txt (ncu --set full): dram read 151.1 MB + write 31.9 MB per launch (B=16)
 
 
 def peaks():
@@ -102,20 +102,25 @@ class ClockSampler:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        rows, mx, reasons = [], 0, set()
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                clk, pw = float(r[0]), float(r[2])
+                mx = max(mx, float(r[1]))
             except (ValueError, IndexError):
                 continue
+            rows.append((clk, pw))
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        sm.sort()
-        # samples under load = upper half (the sampler also sees the idle edges of the region)
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        # samples under load = those drawing at least 60% of the highest power seen (the sampler also sees the idle edges
+        # of the region, where the clock sits at its maximum)
+        pmax = max((pw for _, pw in rows), default=0.0)
+        load = sorted(clk for clk, pw in rows if pw >= 0.6 * pmax) or sorted(clk for clk, _ in rows)
+        pw_load = sorted(pw for _, pw in rows if pw >= 0.6 * pmax)
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_min_mhz": load[0] if load else None, "sm_max_mhz": mx or None,
+                "power_w": pw_load[len(pw_load) // 2] if pw_load else None, "reasons": sorted(reasons), "samples": len(rows),
+                "samples_under_load": len(load)}
 
 
 def run_reference(args, rank):
