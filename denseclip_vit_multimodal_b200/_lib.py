@@ -104,7 +104,7 @@ EXPORTS = [
     "dclip_abi_version", "dclip_create", "dclip_destroy", "dclip_last_error", "dclip_launch_count",
     "dclip_reset_launch_count", "dclip_gemm", "dclip_layernorm", "dclip_cast_bf16", "dclip_attention",
     "dclip_attention_small", "dclip_im2col_patches", "dclip_posemb_interp", "dclip_tap_nchw", "dclip_nchw_to_tokens",
-    "dclip_token_mean", "dclip_score_map", "dclip_upsample_bilinear", "dclip_upsample_argmax", "dclip_gamma_residual", "dclip_conv3x3_gather",
+    "dclip_token_mean", "dclip_score_map", "dclip_upsample_bilinear", "dclip_upsample_argmax", "dclip_eval_stats", "dclip_gamma_residual", "dclip_conv3x3_gather",
     "dclip_vit_create", "dclip_vit_destroy", "dclip_vit_set_weights", "dclip_vit_workspace_bytes", "dclip_vit_forward",
 ]
 
@@ -137,6 +137,7 @@ def _declare(lib):
     lib.dclip_score_map.argtypes = [vp, vp, ll, ll, i, vp, i, i, i, i, f, vp, vp]
     lib.dclip_upsample_bilinear.argtypes = [vp, vp, i, ll, ll, i, i, i, i, i, i, vp, vp]
     lib.dclip_upsample_argmax.argtypes = [vp, vp, ll, ll, i, i, i, i, i, i, vp, vp]
+    lib.dclip_eval_stats.argtypes = [vp, vp, vp, i, ll, i, i, vp, vp, vp, ll, vp, vp, vp]
     lib.dclip_gamma_residual.argtypes = [vp, vp, vp, vp, vp, ll, i, vp]
     lib.dclip_conv3x3_gather.argtypes = [vp, vp, i, ll, ll, i, i, i, i, i, vp, ll, vp]
     lib.dclip_vit_create.argtypes = [vp, C.POINTER(VitConfig), C.POINTER(vp)]

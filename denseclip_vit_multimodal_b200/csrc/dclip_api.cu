@@ -305,6 +305,22 @@ int dclip_upsample_argmax(dclip_handle_t h, const float* in, long long ldi, long
   });
 }
 
+int dclip_eval_stats(dclip_handle_t h, const uint8_t* pred, const void* target, int target_is_i64, long long n, int K,
+                     int ignore_index, const float* depth_pred, const float* depth_gt, const uint8_t* depth_mask,
+                     long long n_depth, long long* conf, double* depth_stats, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(pred || depth_pred, "eval_stats: nothing to do");
+    if (pred) DCLIP_REQUIRE(target && conf && K > 0 && K <= 64 && n >= 0, "eval_stats: segmentation needs target, conf and 0 < K <= 64");
+    if (depth_pred) DCLIP_REQUIRE(depth_gt && depth_stats && n_depth >= 0, "eval_stats: depth needs depth_gt and depth_stats");
+    EvalStatsParams p{pred, target, target_is_i64, n, pred ? K : 1, ignore_index, depth_pred, depth_gt, depth_mask, n_depth,
+                      reinterpret_cast<unsigned long long*>(conf), depth_stats};
+    const long long work = std::max(pred ? n : 0, depth_pred ? n_depth : 0);
+    const int grid = int(std::max<long long>(1, std::min<long long>((work + 256 * 16 - 1) / (256 * 16), 148 * 8)));
+    eval_stats_kernel<<<grid, 256, size_t(p.K) * p.K * sizeof(unsigned int), static_cast<cudaStream_t>(stream)>>>(p);
+    check_launch(h);
+  });
+}
+
 int dclip_gamma_residual(dclip_handle_t h, const float* a, const float* gamma, const float* d, float* out, long long n,
                          int C, void* stream) {
   return guarded(h, [&] {

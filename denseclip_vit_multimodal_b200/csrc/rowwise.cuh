@@ -540,6 +540,59 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(const UpsampleArgm
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Evaluation statistics on the device (reference: torchmetrics JaccardIndex / Accuracy with ignore_index and
+// MeanSquaredError(squared=False) over the masked depth pixels, train_denseclip.py:351-355, 582-593).
+//   conf[t*K + p] += #pixels with target t (!= ignore_index, < K) predicted as p       (int64, accumulated)
+//   depth_stats[0] += sum (pred - gt)^2 over pixels with mask != 0,  depth_stats[1] += their count   (double, accumulated)
+// Block-private shared-memory histogram, one global atomic per non-empty bin per block; integer sums are exact and
+// order-independent, so shards can be reduced with one NCCL all-reduce.
+// ---------------------------------------------------------------------------------------------------------
+struct EvalStatsParams {
+  const uint8_t* pred; const void* target; int target_i64; long long n; int K; int ignore_index;
+  const float* depth_pred; const float* depth_gt; const uint8_t* depth_mask; long long n_depth;
+  unsigned long long* conf; double* depth_stats;
+};
+
+__global__ void __launch_bounds__(256) eval_stats_kernel(const EvalStatsParams p) {
+  extern __shared__ unsigned int hist[];  // [K*K]
+  const int KK = p.K * p.K;
+  for (int i = threadIdx.x; i < KK; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x, first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p.pred) {
+    for (long long i = first; i < p.n; i += stride) {
+      const long long t = p.target_i64 ? reinterpret_cast<const long long*>(p.target)[i] : (long long)reinterpret_cast<const uint8_t*>(p.target)[i];
+      const int pr = p.pred[i];
+      if (t != p.ignore_index && t >= 0 && t < p.K && pr < p.K) atomicAdd(&hist[int(t) * p.K + pr], 1u);
+    }
+  }
+  double se = 0.0, cnt = 0.0;
+  if (p.depth_pred) {
+    for (long long i = first; i < p.n_depth; i += stride) {
+      if (!p.depth_mask || p.depth_mask[i]) {
+        const double d = double(p.depth_pred[i]) - double(p.depth_gt[i]);
+        se += d * d;
+        cnt += 1.0;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < KK; i += blockDim.x)
+    if (hist[i]) atomicAdd(&p.conf[i], (unsigned long long)hist[i]);
+  if (p.depth_pred) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      se += __shfl_xor_sync(0xffffffffu, se, o);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0.0) {
+      atomicAdd(&p.depth_stats[0], se);
+      atomicAdd(&p.depth_stats[1], cnt);
+    }
+  }
+}
+
 // out[i] = a[i] + gamma[i % C] * d[i]     (text + gamma * text_diff, denseclip.py:665)
 __global__ void gamma_residual_kernel(const float* __restrict__ a, const float* __restrict__ g, const float* __restrict__ d,
                                       float* __restrict__ out, long long n, int C) {

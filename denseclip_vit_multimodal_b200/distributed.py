@@ -50,6 +50,17 @@ def confusion_matrix(pred: torch.Tensor, target: torch.Tensor, num_classes: int,
     return torch.bincount(idx, minlength=num_classes * num_classes).reshape(num_classes, num_classes)
 
 
+def shard_eval_stats(pred: torch.Tensor, target: torch.Tensor, num_classes: int, ignore_index: int = 255, depth_pred=None,
+                     depth_gt=None, depth_mask=None):
+    """Evaluation statistics of the local shard, computed by the native kernel (`ops.eval_stats`, one pass over the uint8
+    class map / depth map, nothing leaves the GPU): (conf int64 [K, K], depth_sq_err_sum float64 [], depth_count float64 []),
+    ready for `reduce_eval_stats`.  Reference: torchmetrics JaccardIndex / Accuracy(ignore_index) and masked RMSE
+    (train_denseclip.py:351-355, 582-593)."""
+    from . import ops
+    conf, ds = ops.eval_stats(pred, target, num_classes, ignore_index, depth_pred, depth_gt, depth_mask)
+    return conf, ds[0].clone(), ds[1].clone()
+
+
 def reduce_eval_stats(conf: torch.Tensor, depth_sq_err_sum: torch.Tensor, depth_count: torch.Tensor, group=None):
     """All-reduce (sum) the evaluation statistics of all shards: 19x19 confusion matrix + depth squared-error sum/count.
     Returns (conf, mIoU, pixel_acc, rmse)."""

@@ -226,6 +226,53 @@ def upsample_argmax(x: torch.Tensor, size, *, tokens_hw, channels) -> torch.Tens
     return out
 
 
+def eval_stats(pred=None, target=None, num_classes: int = 19, ignore_index: int = 255, depth_pred=None, depth_gt=None,
+               depth_mask=None, conf=None, depth_stats=None):
+    """Accumulate one shard's evaluation statistics on the device: int64 confusion matrix [K, K]
+    (rows = target, cols = prediction, `ignore_index` skipped) and float64 [sum squared depth error, count] over
+    `depth_mask`.  `conf` / `depth_stats` are created zeroed when not passed, accumulated into when passed."""
+    ref = pred if pred is not None else depth_pred
+    if ref is None:
+        raise DclipError("eval_stats: pass pred/target and/or depth_pred/depth_gt")
+    dev = ref.device
+    if conf is None:
+        conf = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=dev)
+    if depth_stats is None:
+        depth_stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    _req(conf, torch.int64, "conf")
+    _req(depth_stats, torch.float64, "depth_stats")
+    p_ptr = t_ptr = dp_ptr = dg_ptr = dm_ptr = None
+    n = nd = 0
+    t_i64 = 0
+    keep = []
+    if pred is not None:
+        pred = _req(pred.contiguous(), torch.uint8, "pred")
+        if target is None or target.numel() != pred.numel():
+            raise DclipError("eval_stats: target must have as many pixels as pred")
+        if target.dtype not in (torch.uint8, torch.int64):
+            raise DclipError(f"eval_stats: target must be uint8 or int64, got {target.dtype}")
+        target = _req(target.contiguous(), target.dtype, "target")
+        p_ptr, t_ptr, n, t_i64 = _ptr(pred), _ptr(target), pred.numel(), int(target.dtype == torch.int64)
+        keep += [pred, target]
+    if depth_pred is not None:
+        depth_pred = _req(depth_pred.contiguous(), torch.float32, "depth_pred")
+        if depth_gt is None or depth_gt.numel() != depth_pred.numel():
+            raise DclipError("eval_stats: depth_gt must have as many pixels as depth_pred")
+        depth_gt = _req(depth_gt.contiguous(), torch.float32, "depth_gt")
+        dp_ptr, dg_ptr, nd = _ptr(depth_pred), _ptr(depth_gt), depth_pred.numel()
+        keep += [depth_pred, depth_gt]
+        if depth_mask is not None:
+            if depth_mask.numel() != nd:
+                raise DclipError("eval_stats: depth_mask must have as many pixels as depth_pred")
+            depth_mask = depth_mask.contiguous()
+            depth_mask = depth_mask.view(torch.uint8) if depth_mask.dtype == torch.bool else _req(depth_mask, torch.uint8, "depth_mask")
+            dm_ptr = _ptr(depth_mask)
+            keep.append(depth_mask)
+    _call(ref, _lib.lib().dclip_eval_stats, p_ptr, t_ptr, t_i64, n, int(conf.shape[0]), int(ignore_index), dp_ptr, dg_ptr, dm_ptr, nd,
+          _ptr(conf), _ptr(depth_stats), _stream(ref))
+    return conf, depth_stats
+
+
 def gamma_residual(a: torch.Tensor, gamma: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
     a = _req(a.contiguous(), torch.float32, "a")
     d = _req(d.contiguous(), torch.float32, "d")

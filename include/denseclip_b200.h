@@ -119,6 +119,14 @@ int dclip_upsample_bilinear(dclip_handle_t h, const float* in, int in_nchw, long
  * (simple_test's seg_logit.argmax(dim=1), denseclip.py:987-1000, without materialising the logits) */
 int dclip_upsample_argmax(dclip_handle_t h, const float* in, long long ldi, long long in_bs, int B, int K, int hh, int ww,
                           int H, int W, uint8_t* out, void* stream);
+/* evaluation statistics of one shard, accumulated into caller-zeroed buffers (train_denseclip.py:351-355, 582-593:
+ * torchmetrics JaccardIndex / Accuracy with ignore_index, MeanSquaredError(squared=False) over depth_mask):
+ * conf[t*K + p] += 1 for every pixel with target t != ignore_index (int64 [K*K], K <= 64; target uint8 or int64);
+ * depth_stats[0] += sum (depth_pred - depth_gt)^2 and depth_stats[1] += count over pixels with depth_mask != 0
+ * (mask may be NULL = all pixels).  Either half may be skipped by passing pred == NULL / depth_pred == NULL. */
+int dclip_eval_stats(dclip_handle_t h, const uint8_t* pred, const void* target, int target_is_i64, long long n, int K,
+                     int ignore_index, const float* depth_pred, const float* depth_gt, const uint8_t* depth_mask,
+                     long long n_depth, long long* conf, double* depth_stats, void* stream);
 int dclip_gamma_residual(dclip_handle_t h, const float* a, const float* gamma, const float* d, float* out, long long n,
                          int C, void* stream);
 /* 3x3 / pad 1 / stride 1 conv operand gather: in token-major [B][row0 + y*w + x][ld] (fp32 or bf16, C channels) ->

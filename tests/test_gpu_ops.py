@@ -163,3 +163,39 @@ def test_ops_reject_bad_inputs(ops):
         ops.gemm(a.float(), a, want_f32=True)                                                     # wrong dtype
     with pytest.raises(DclipError):
         ops.layernorm(torch.zeros(2, 100, device="cuda"), torch.ones(100, device="cuda"), torch.zeros(100, device="cuda"), want_f32=True)
+
+
+@pytest.mark.parametrize("K,tdtype", [(19, torch.int64), (19, torch.uint8), (5, torch.int64), (64, torch.uint8)])
+def test_eval_stats_kernel(ops, K, tdtype):
+    """Native evaluation statistics against the torch definitions: confusion matrix with ignore_index
+    (bit-exact, integer) and masked squared depth error / count (float64)."""
+    from denseclip_vit_multimodal_b200.distributed import confusion_matrix, reduce_eval_stats, shard_eval_stats
+    g = torch.Generator().manual_seed(40 + K)
+    B, H, W = 3, 37, 52
+    pred = torch.randint(0, K, (B, H, W), generator=g).to(torch.uint8).cuda()
+    target = torch.randint(0, K, (B, H, W), generator=g)
+    target[torch.rand(B, H, W, generator=g) < 0.1] = 255        # ignore_index
+    target = target.to(tdtype).cuda()
+    dp = torch.randn(B, 1, H, W, generator=g).cuda()
+    dg = (torch.rand(B, 1, H, W, generator=g) * 80).cuda()
+    mask = (torch.rand(B, 1, H, W, generator=g) < 0.7).cuda()
+    conf, ds = ops.eval_stats(pred, target, K, 255, dp, dg, mask)
+    assert torch.equal(conf, confusion_matrix(pred, target, K, 255))
+    err = (dp.double() - dg.double())[mask]
+    assert float(ds[1]) == float(mask.sum())
+    assert abs(float(ds[0]) - float((err * err).sum())) <= 1e-9 * float((err * err).sum())
+    # accumulation into caller buffers, segmentation-only and depth-only calls, unmasked depth
+    ops.eval_stats(pred, target, K, 255, conf=conf, depth_stats=ds)
+    assert torch.equal(conf, 2 * confusion_matrix(pred, target, K, 255)) and float(ds[1]) == float(mask.sum())
+    _, ds2 = ops.eval_stats(depth_pred=dp, depth_gt=dg)
+    assert float(ds2[1]) == dp.numel()
+    # all pixels ignored / empty mask leave the buffers untouched
+    c0, d0 = ops.eval_stats(pred, torch.full_like(target, 255), K, 255, dp, dg, torch.zeros_like(mask))
+    assert int(c0.sum()) == 0 and float(d0.sum()) == 0.0
+    c, se, n = shard_eval_stats(pred, target, K, 255, dp, dg, mask)
+    _, miou, acc, rmse = reduce_eval_stats(c, se, n)
+    tp = conf.diag().double() / 2
+    assert abs(acc - float(tp.sum() / (conf.sum() / 2))) < 1e-12 and 0.0 <= miou <= 1.0
+    assert abs(rmse - float(err.pow(2).mean().sqrt())) < 1e-9
+    with pytest.raises(Exception):
+        ops.eval_stats(pred, target.float(), K)
