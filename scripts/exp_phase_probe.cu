@@ -11,15 +11,61 @@
 #include "ptx.cuh"
 using namespace dclip;
 
-template <int NC, int VARIANT>
+// NEIGHBOUR workloads for the second warp of every sub-partition (threads >= 128) while warps 0-3 run the exponential phase:
+// 1 = dependent FMNMX/FADD chain (ALU issue pressure), 2 = mbarrier.try_wait spin on a barrier that never completes,
+// 3 = tcgen05.ld.x32 + wait::ld loop, 4 = 64 FMNMX3 then a 32-thread named barrier (bursty, like the load/max phase)
+template <int NEIGHBOUR>
+__device__ __forceinline__ float neighbour_work(volatile int* stop, uint64_t* bar, uint32_t taddr, int lane) {
+  float a = lane * 0.001f, b = 1.0f + lane;
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = lane + i;
+  while (!*stop) {
+    if (NEIGHBOUR == 1) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) { a = fmaxf(a, b + i); b = fminf(b, a - i); }
+    } else if (NEIGHBOUR == 2) {
+      a += mbar_try_wait(bar, 0) ? 1.f : 0.f;
+    } else if (NEIGHBOUR == 3) {
+      tmem_ld_32x32b_x32(taddr, v);
+      tmem_wait_ld();
+      a += __uint_as_float(v[0]);
+    } else if (NEIGHBOUR == 4) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) a = fmaxf(a, fmaxf(__uint_as_float(v[i]) + b, __uint_as_float(v[i + 1]) - b));
+      b += a;
+      named_bar_sync(1 + (threadIdx.x >> 5) % 4, 32);
+    }
+  }
+  return a + b;
+}
+
+template <int NC, int VARIANT, int NEIGHBOUR = 0>
 __global__ void __launch_bounds__(256, 1) probe(const float* in, uint32_t* out, long long* cyc, int iters, float sc, int z) {
+  __shared__ __align__(8) uint64_t nbar;
+  __shared__ uint32_t tslot;
+  __shared__ volatile int stop;
+  if (NEIGHBOUR) {
+    if (threadIdx.x == 0) { mbar_init(&nbar, 1); fence_barrier_init(); stop = 0; }
+    if (threadIdx.x < 32) { tmem_alloc(&tslot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x >= 128) {
+      const float r = neighbour_work<NEIGHBOUR>(&stop, &nbar, tslot + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16), threadIdx.x & 31);
+      out[blockIdx.x * blockDim.x + threadIdx.x] = __float_as_uint(r);
+      tc_fence_before();
+      __syncthreads();
+      return;
+    }
+  }
   uint32_t su[NC];
   const float* src = in + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * NC;
 #pragma unroll
   for (int e = 0; e < NC; ++e) su[e] = __float_as_uint(src[e]);
   float l = 0.f, m_used = 1.0f;
   uint32_t sink = 0;
-  __syncthreads();
+  if (NEIGHBOUR) named_bar_sync(9, 128); else __syncthreads();
   const long long t0 = clock64();
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) {
@@ -100,9 +146,16 @@ __global__ void __launch_bounds__(256, 1) probe(const float* in, uint32_t* out, 
   const long long t1 = clock64();
   out[blockIdx.x * blockDim.x + threadIdx.x] = sink + __float_as_uint(l);
   if ((threadIdx.x & 31) == 0) cyc[blockIdx.x * 16 + (threadIdx.x >> 5)] = t1 - t0;
+  if (NEIGHBOUR) {
+    named_bar_sync(9, 128);
+    if (threadIdx.x == 0) stop = 1;
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tslot, 512); }
+  }
 }
 
-template <int NC, int VARIANT>
+template <int NC, int VARIANT, int NEIGHBOUR = 0>
 void run(int warps) {
   const int threads = warps * 32, iters = 2000;
   float* in; uint32_t* out; long long* cyc;
@@ -110,14 +163,14 @@ void run(int warps) {
   cudaMemset(in, 0, (size_t)148 * 256 * NC * 4);
   cudaMalloc(&out, 148 * 256 * 4);
   cudaMalloc(&cyc, 148 * 16 * 8);
-  probe<NC, VARIANT><<<148, threads>>>(in, out, cyc, iters, 0.18f, 0);
-  probe<NC, VARIANT><<<148, threads>>>(in, out, cyc, iters, 0.18f, 0);
+  probe<NC, VARIANT, NEIGHBOUR><<<148, NEIGHBOUR ? 256 : threads>>>(in, out, cyc, iters, 0.18f, 0);
+  probe<NC, VARIANT, NEIGHBOUR><<<148, NEIGHBOUR ? 256 : threads>>>(in, out, cyc, iters, 0.18f, 0);
   cudaDeviceSynchronize();
   long long h[16];
   cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
   const double per_tile = (double)h[0] / iters;
   const double mufu_per_smsp = (double)NC * (warps / 4.0);  // MUFU warp-instructions per sub-partition per iteration
-  printf("variant %d NC=%3d  %d warp(s)/sub-partition: %7.1f cycles per tile-row pass  -> %5.2f cycles per MUFU instr per sub-partition\n", VARIANT, NC,
+  printf("variant %d neighbour %d NC=%3d  %d warp(s)/sub-partition: %7.1f cycles per tile-row pass  -> %5.2f cycles per MUFU instr per sub-partition\n", VARIANT, NEIGHBOUR, NC,
          warps / 4, per_tile, per_tile / mufu_per_smsp);
   cudaFree(in); cudaFree(out); cudaFree(cyc);
 }
@@ -126,6 +179,7 @@ int main() {
   run<128, 0>(4); run<128, 0>(8);
   run<64, 0>(4); run<64, 0>(8);
   run<128, 1>(4); run<128, 1>(8);
+  run<128, 0, 1>(4); run<128, 0, 2>(4); run<128, 0, 3>(4); run<128, 0, 4>(4);
   cudaError_t e = cudaDeviceSynchronize();
   printf("%s\n", cudaGetErrorString(e));
   return e != cudaSuccess;
