@@ -30,6 +30,22 @@ __device__ __forceinline__ float neighbour_work(volatile int* stop, uint64_t* ba
       tmem_ld_32x32b_x32(taddr, v);
       tmem_wait_ld();
       a += __uint_as_float(v[0]);
+    } else if (NEIGHBOUR == 5) {
+      named_bar_sync(1 + (threadIdx.x >> 5) % 4, 32);
+    } else if (NEIGHBOUR == 6) {  // 3-input max (FMNMX3), four independent chains, no barrier
+      float m0 = a, m1 = b, m2 = a, m3 = b;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]) + b, __uint_as_float(v[i + 1]) - b));
+        m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]) + b, __uint_as_float(v[i + 3]) - b));
+        m2 = fmaxf(m2, fmaxf(__uint_as_float(v[i + 4]) + b, __uint_as_float(v[i + 5]) - b));
+        m3 = fmaxf(m3, fmaxf(__uint_as_float(v[i + 6]) + b, __uint_as_float(v[i + 7]) - b));
+      }
+      a = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      b += a;
+    } else if (NEIGHBOUR == 7) {  // __syncwarp + predicated single-lane mbarrier arrive (the s_free / p_ready pattern)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
     } else if (NEIGHBOUR == 4) {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) a = fmaxf(a, fmaxf(__uint_as_float(v[i]) + b, __uint_as_float(v[i + 1]) - b));
@@ -179,7 +195,7 @@ int main() {
   run<128, 0>(4); run<128, 0>(8);
   run<64, 0>(4); run<64, 0>(8);
   run<128, 1>(4); run<128, 1>(8);
-  run<128, 0, 1>(4); run<128, 0, 2>(4); run<128, 0, 3>(4); run<128, 0, 4>(4);
+  run<128, 0, 1>(4); run<128, 0, 2>(4); run<128, 0, 3>(4); run<128, 0, 4>(4); run<128, 0, 5>(4); run<128, 0, 6>(4); run<128, 0, 7>(4);
   cudaError_t e = cudaDeviceSynchronize();
   printf("%s\n", cudaGetErrorString(e));
   return e != cudaSuccess;
