@@ -1,6 +1,7 @@
 // Host-side helpers: error plumbing, driver entry point for cuTensorMapEncodeTiled (no link-time libcuda
 // dependency, so the library loads on a machine without a driver), tensor-map builders, GEMM launcher.
 #pragma once
+#include <set>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
@@ -151,6 +152,18 @@ inline void launch_gemm_inst(const GemmPlan& plan, cudaStream_t stream) {
   DCLIP_CHECK_CUDA(cudaGetLastError());
 }
 
+// DCLIP_GEMM_TRACE=1: print every (BLOCK_N, act, epilogue flags, pair) combination that falls through to the generic
+// runtime-checked epilogue, once -- those are ~5x slower per tile than a specialised instantiation
+inline void trace_generic_gemm(int bn, int act, int flags, int pair, const GemmParams& p) {
+  static const bool on = [] { const char* e = getenv("DCLIP_GEMM_TRACE"); return e && e[0] == '1'; }();
+  if (!on) return;
+  static std::set<long long> seen;
+  const long long key = ((long long)bn << 32) | (act << 16) | (flags << 4) | pair;
+  if (seen.insert(key).second)
+    fprintf(stderr, "dclip gemm: generic epilogue bn=%d act=%d flags=%d pair=%d (M=%d N=%d K=%d split_in=%d)\n", bn, act, flags, pair, p.M,
+            p.N, p.K, p.split_in);
+}
+
 template <int BN>
 inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
   const GemmParams& p = plan.p;
@@ -177,6 +190,10 @@ inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
         return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32, true>(plan, stream);
       if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32 | EPI_OUT_BF16))
         return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32 | EPI_OUT_BF16, true>(plan, stream);
+      if (p.act == ACT_NONE && flags == EPI_OUT_F32) return launch_gemm_inst<BN, ACT_NONE, EPI_OUT_F32, true>(plan, stream);
+      if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32 | EPI_REMAP))  // patch embedding (+ positional embedding, row remap)
+        return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32 | EPI_REMAP, true>(plan, stream);
+      trace_generic_gemm(BN, p.act, flags, 1, p);
       return launch_gemm_inst<BN, -1, -1, true>(plan, stream);
     }
   }
@@ -193,6 +210,12 @@ inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
   if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32 | EPI_OUT_BF16))
     return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32 | EPI_OUT_BF16>(plan, stream);
   if (p.act == ACT_RELU && flags == EPI_OUT_BF16) return launch_gemm_inst<BN, ACT_RELU, EPI_OUT_BF16>(plan, stream);
+  if (p.act == ACT_NONE && flags == EPI_OUT_F32) return launch_gemm_inst<BN, ACT_NONE, EPI_OUT_F32>(plan, stream);
+  if (p.act == ACT_RELU && flags == (EPI_OUT_F32 | EPI_OUT_BF16)) return launch_gemm_inst<BN, ACT_RELU, EPI_OUT_F32 | EPI_OUT_BF16>(plan, stream);
+  if (p.act == ACT_RELU && flags == EPI_OUT_F32) return launch_gemm_inst<BN, ACT_RELU, EPI_OUT_F32>(plan, stream);
+  if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32 | EPI_REMAP))
+    return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32 | EPI_REMAP>(plan, stream);
+  trace_generic_gemm(BN, p.act, flags, 0, p);
   return launch_gemm_inst<BN, -1, -1>(plan, stream);
   }
 }
