@@ -253,6 +253,10 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
   const int num_m_pairs = ((p.M + 127) / 128 + 1) / 2;
   if (bn == 0) {
     bn = p.N > 128 ? 256 : (p.N > 64 ? 128 : 64);
+    // latency-bound tiny problems (the ContextDecoder's M = 304 rows): narrow tiles spread the W traffic and the epilogue
+    // over 4x more CTAs (measured in a CUDA graph: 10.9 -> 7.2 us, 14.8 -> 8.7 us per launch)
+    static const bool no_small = [] { const char* e = getenv("DCLIP_GEMM_NO_SMALL_BN"); return e && e[0] == '1'; }();
+    if (!no_small && p.conv_C == 0 && (long long)((p.M + 127) / 128) * ((p.N + 255) / 256) * 8 <= sm_count()) bn = 64;
     // wave quantisation of the CTA-pair grid: N = 768 with M = 32784 is 387 pair tiles of 256x256 on 74 pairs (6 waves, 87%
     // full) but 516 tiles of 256x192 (7 waves, 99.6% full).  Only the fp32-residual epilogues are instantiated at 192, and
     // only short-K GEMMs win (measured, B200: K = 768 0.062 -> 0.054 ms; K = 3072 0.136 -> 0.140 ms, the narrower tile
