@@ -135,6 +135,29 @@ __global__ void __launch_bounds__(256) im2col_patch_kernel(const Im2colParams p)
   }
 }
 
+// Vector path (ps % 8 == 0, W % 4 == 0, 16-byte aligned image): a thread converts 8 consecutive pixels of one patch row
+// (two 128-bit loads, one 128-bit store per output half) -- 4x fewer threads and index decodes than the 2-pixel kernel.
+__global__ void __launch_bounds__(256) im2col_patch_vec8_kernel(const Im2colParams p) {
+  const int K = 3 * p.ps * p.ps, K8 = K >> 3, ps8 = p.ps >> 3;
+  const long long total = (long long)p.B * p.gh * p.gw * K8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / K8;
+    const int k8 = int(i - row * K8);
+    const int c = k8 / (p.ps * ps8), rem = k8 - c * p.ps * ps8, ky = rem / ps8, kx = (rem - ky * ps8) * 8;
+    const int b = int(row / (p.gh * p.gw)), pr = int(row - (long long)b * p.gh * p.gw), py = pr / p.gw, px = pr - py * p.gw;
+    const float4* src = reinterpret_cast<const float4*>(p.img + (((long long)b * 3 + c) * p.H + (py * p.ps + ky)) * p.W + px * p.ps + kx);
+    const float4 a = __ldcs(src), bb = __ldcs(src + 1);
+    const uint32_t h0 = pack_bf16x2(a.x, a.y), h1 = pack_bf16x2(a.z, a.w), h2 = pack_bf16x2(bb.x, bb.y), h3 = pack_bf16x2(bb.z, bb.w);
+    const int k = c * p.ps * p.ps + ky * p.ps + kx;
+    *reinterpret_cast<uint4*>(p.out + row * p.lda + k) = make_uint4(h0, h1, h2, h3);
+    if (p.split) {
+      auto lo = [](float x, float y, uint32_t h) { return pack_bf16x2(x - __uint_as_float(h << 16), y - __uint_as_float(h & 0xffff0000u)); };
+      *reinterpret_cast<uint4*>(p.out + row * p.lda + p.split_off + k) =
+          make_uint4(lo(a.x, a.y, h0), lo(a.z, a.w, h1), lo(bb.x, bb.y, h2), lo(bb.z, bb.w, h3));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Positional-embedding interpolation (models.py:514-540): pos [1+g0*g0, D] -> out [1+gh*gw, D];
 // row 0 copied, the g0 x g0 grid resized bilinearly with align_corners=False (ATen upsample_bilinear2d index rule:
@@ -620,6 +643,13 @@ inline void launch_layernorm(const LayerNormParams& p, cudaStream_t stream) {
 }
 
 inline void launch_im2col(const Im2colParams& p, cudaStream_t stream) {
+  if (p.ps % 8 == 0 && p.W % 4 == 0 && p.lda % 8 == 0 && p.split_off % 8 == 0 && (reinterpret_cast<uintptr_t>(p.img) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+    const long long total8 = (long long)p.B * p.gh * p.gw * (3 * p.ps * p.ps / 8);
+    const int grid8 = int(total8 / 256 < 148 * 16 ? (total8 + 255) / 256 : 148 * 16);
+    im2col_patch_vec8_kernel<<<grid8 > 0 ? grid8 : 1, 256, 0, stream>>>(p);
+    return;
+  }
   const long long total = (long long)p.B * p.gh * p.gw * (3 * p.ps * p.ps / 2);
   const int grid = int(total / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   im2col_patch_kernel<<<grid > 0 ? grid : 1, 256, 0, stream>>>(p);

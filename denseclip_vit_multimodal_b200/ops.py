@@ -107,6 +107,19 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, K: int | None = None, split_in: bo
     return out_f32, out_bf16
 
 
+def im2col_patches(img: torch.Tensor, ps: int, *, split: bool = False) -> torch.Tensor:
+    """Patch-embed operand gather (Conv2d(3, D, ps, stride=ps), models.py:407, 546-548): fp32 [B, 3, H, W] ->
+    bf16 [B*gh*gw, K (2K = hi|lo with split)], K index = c*ps*ps + ky*ps + kx; trailing pixels that do not fill a patch are dropped."""
+    img = _req(img.contiguous(), torch.float32, "img")
+    B, Cc, H, W = img.shape
+    if Cc != 3 or ps % 2:
+        raise DclipError("im2col_patches: 3 input channels and an even patch size are required")
+    gh, gw, K = H // ps, W // ps, 3 * ps * ps
+    out = torch.empty(B * gh * gw, K * (2 if split else 1), dtype=torch.bfloat16, device=img.device)
+    _call(img, _lib.lib().dclip_im2col_patches, _ptr(img), B, H, W, ps, _ptr(out), out.stride(0), int(split), K, _stream(img))
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma, beta, eps: float = 1e-5, *, want_f32=False, want_bf16=False, split=False,
               out_f32=None, out_bf16=None):
     """LayerNorm over the last dim of fp32 [M, D]. bf16 output is [M, D] or, with split, [M, 2D] = hi|lo."""

@@ -199,3 +199,17 @@ def test_eval_stats_kernel(ops, K, tdtype):
     assert abs(rmse - float(err.pow(2).mean().sqrt())) < 1e-9
     with pytest.raises(Exception):
         ops.eval_stats(pred, target.float(), K)
+
+
+@pytest.mark.parametrize("ps,H,W", [(16, 64, 96), (16, 40, 52), (14, 50, 76), (8, 32, 40)])   # vector path, ragged, scalar path (ps 14), ps 8
+@pytest.mark.parametrize("split", [False, True])
+def test_im2col_patches(ops, ps, H, W, split):
+    """Patch-embed operand gather against F.unfold (K order = conv1.weight flattening; trailing pixels dropped)."""
+    img = _rand(2, 3, H, W, seed=50 + ps)
+    got = ops.im2col_patches(img, ps, split=split)
+    gh, gw, K = H // ps, W // ps, 3 * ps * ps
+    ref = F.unfold(img[:, :, :gh * ps, :gw * ps], kernel_size=ps, stride=ps).transpose(1, 2).reshape(-1, K)
+    hi = ref.bfloat16()
+    assert torch.equal(got[:, :K], hi)
+    if split:
+        assert torch.equal(got[:, K:], (ref - hi.float()).bfloat16())
