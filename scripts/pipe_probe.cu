@@ -90,6 +90,13 @@ __global__ void __launch_bounds__(256, 1) probe(float* out, long long* cyc, int 
         const unsigned long long h2 = pk2(0.5f, 0.5f), s2 = pk2(seed, seed);
         upk2(fma2(pk2(x[i], x[i + 1]), h2, s2), x[i], x[i + 1]);
         upk2(fma2(pk2(x[i], x[i + 1]), h2, s2), x[i], x[i + 1]);
+      } else if (MODE == 9) {  // ex2.approx.ftz.bf16x2: two MUFU.EX2.BF16 + PRMT per instruction -- is the half-precision SFU op any faster?
+        unsigned int v = __float_as_uint(x[i]), w;
+        asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(w) : "r"(v));
+        x[i] = __uint_as_float(w & 0xbfffbfffu);
+        unsigned int v2 = __float_as_uint(x[i + 1]), w2;
+        asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(w2) : "r"(v2));
+        x[i + 1] = __uint_as_float(w2 & 0xbfffbfffu);
       } else if (MODE == 6) {  // as 5 with the integer pack
         float a = fmaf(x[i], 0.5f, seed), b = fmaf(x[i + 1], 0.5f, seed);
         a = ex2(a);
@@ -140,6 +147,7 @@ int main() {
   run<4>("ex2 x2 + fma x2", 1);
   run<5>("fma x2 + ex2 x2 + cvt + add x2", 1);
   run<6>("fma x2 + ex2 x2 + int pack + add x2", 1);
+  run<9>("ex2.bf16x2 x2 (= 4 MUFU.EX2.BF16)", 0);
   run<0>("ex2 x2", 1, 128);
   run<2>("ex2 x2 + cvt.bf16x2", 1, 128);
   run<4>("ex2 x2 + fma x2", 1, 128);
