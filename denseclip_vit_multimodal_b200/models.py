@@ -362,11 +362,10 @@ def _text_transformer_native(x: torch.Tensor, packed: _PackedBlocks, heads: int,
             _, h = ops.layernorm(x, l["ln1_g"], l["ln1_b"], want_bf16=True, split=True)
             qkv, _ = ops.gemm(h, l["in_w"], split_in=True, bias=l["in_b"], want_f32=True)
             q3 = qkv.view(n_seq, seq_len, 3 * D)
-            att = torch.empty(n_seq, seq_len, D, dtype=torch.float32, device=x.device)
+            att = torch.empty(n_seq, seq_len, 2 * D, dtype=torch.bfloat16, device=x.device)   # hi|lo written by the kernel
             ops.attention_small(q3, q3, q3, B=n_seq, H=heads, q_first=0, q_count=seq_len, Nk=seq_len, q_col0=0, k_col0=D,
-                                v_col0=2 * D, scale=64 ** -0.5, out=att, causal=True)
-            a = ops.split_bf16(att.view(-1, D))
-            ops.gemm(a, l["out_w"], split_in=True, bias=l["out_b"], residual=x, out_f32=x)
+                                v_col0=2 * D, scale=64 ** -0.5, out=att, causal=True, out_split_off=D)
+            ops.gemm(att.view(-1, 2 * D), l["out_w"], split_in=True, bias=l["out_b"], residual=x, out_f32=x)
             _, h = ops.layernorm(x, l["ln2_g"], l["ln2_b"], want_bf16=True, split=True)
             _, g = ops.gemm(h, l["fc_w"], split_in=True, bias=l["fc_b"], act="quickgelu_precise", want_bf16=True, split_out=True)
             ops.gemm(g, l["pj_w"], split_in=True, bias=l["pj_b"], residual=x, out_f32=x)
@@ -593,6 +592,11 @@ class ContextDecoder(nn.Module):
                 ca_kv=pw(torch.cat([l.cross_attn.k_proj.weight, l.cross_attn.v_proj.weight], 0)),
                 ca_kv_b=_cat_bias(l.cross_attn.k_proj, l.cross_attn.v_proj),
                 ca_o=pw(l.cross_attn.proj.weight), fc=pw(l.mlp[0].weight), pj=pw(l.mlp[3].weight)))
+        if len(self.decoder):
+            # the memory does not change across layers: K/V projections of ALL layers run as one GEMM (N = layers * 2 * Wd)
+            p["ca_kv_all"] = pw(torch.cat([torch.cat([l.cross_attn.k_proj.weight, l.cross_attn.v_proj.weight], 0) for l in self.decoder], 0))
+            kvb = [lp["ca_kv_b"] for lp in p["layers"]]
+            p["ca_kv_all_b"] = None if any(b is None for b in kvb) else torch.cat(kvb).contiguous()
         self._packed = p
         return p
 
@@ -621,27 +625,35 @@ class ContextDecoder(nn.Module):
         _, ht = ops.layernorm(t2, g, b, e, want_bf16=True, split=True)
         x, _ = ops.gemm(ht, pk["txt_w"], split_in=True, bias=_f32(self.text_proj[1].bias), want_f32=True)  # [B*K, Wd]
         dev = x.device
-        for l, lp in zip(self.decoder, pk["layers"]):
+        L = len(self.decoder)
+        kv_all = None
+        if L and (pk["ca_kv_all_b"] is not None or all(lp["ca_kv_b"] is None for lp in pk["layers"])):
+            kv_all, _ = ops.gemm(mem, pk["ca_kv_all"], split_in=True, bias=pk["ca_kv_all_b"], want_f32=True)   # [B*N, L*2*Wd]
+            kv_all = kv_all.view(B, N, L * 2 * Wd)
+        att = torch.empty(B, K, 2 * Wd, dtype=torch.bfloat16, device=dev)   # attention output, written as hi|lo by the kernel
+        for li, (l, lp) in enumerate(zip(self.decoder, pk["layers"])):
             sc = l.self_attn.scale
             # self attention on the K text tokens
             g, b, e = ln(l.norm1)
             _, h1 = ops.layernorm(x, g, b, e, want_bf16=True, split=True)
             qkv, _ = ops.gemm(h1, lp["sa_qkv"], split_in=True, bias=lp["sa_qkv_b"], want_f32=True)
             q3 = qkv.view(B, K, 3 * Wd)
-            att = torch.empty(B, K, Wd, dtype=torch.float32, device=dev)
             ops.attention_small(q3, q3, q3, B=B, H=heads, q_first=0, q_count=K, Nk=K, q_col0=0, k_col0=Wd, v_col0=2 * Wd,
-                                scale=sc, out=att)
-            ops.gemm(ops.split_bf16(att.view(-1, Wd)), lp["sa_o"], split_in=True, bias=_f32(l.self_attn.proj.bias), residual=x, out_f32=x)
+                                scale=sc, out=att, out_split_off=Wd)
+            ops.gemm(att.view(-1, 2 * Wd), lp["sa_o"], split_in=True, bias=_f32(l.self_attn.proj.bias), residual=x, out_f32=x)
             # cross attention: text queries over the visual memory
             sc = l.cross_attn.scale
             g, b, e = ln(l.norm2)
             _, h2 = ops.layernorm(x, g, b, e, want_bf16=True, split=True)
             q, _ = ops.gemm(h2, lp["ca_q"], split_in=True, bias=lp["ca_q_b"], want_f32=True)
-            kv, _ = ops.gemm(mem, lp["ca_kv"], split_in=True, bias=lp["ca_kv_b"], want_f32=True)  # [B*N, 2*Wd]
-            kv3 = kv.view(B, N, 2 * Wd)
-            ops.attention_small(q.view(B, K, Wd), kv3, kv3, B=B, H=heads, q_first=0, q_count=K, Nk=N, q_col0=0, k_col0=0,
-                                v_col0=Wd, scale=sc, out=att)
-            ops.gemm(ops.split_bf16(att.view(-1, Wd)), lp["ca_o"], split_in=True, bias=_f32(l.cross_attn.proj.bias), residual=x, out_f32=x)
+            if kv_all is not None:
+                kv3, kc0 = kv_all, li * 2 * Wd
+            else:
+                kv, _ = ops.gemm(mem, lp["ca_kv"], split_in=True, bias=lp["ca_kv_b"], want_f32=True)  # [B*N, 2*Wd]
+                kv3, kc0 = kv.view(B, N, 2 * Wd), 0
+            ops.attention_small(q.view(B, K, Wd), kv3, kv3, B=B, H=heads, q_first=0, q_count=K, Nk=N, q_col0=0, k_col0=kc0,
+                                v_col0=kc0 + Wd, scale=sc, out=att, out_split_off=Wd)
+            ops.gemm(att.view(-1, 2 * Wd), lp["ca_o"], split_in=True, bias=_f32(l.cross_attn.proj.bias), residual=x, out_f32=x)
             # MLP with exact (erf) GELU
             g, b, e = ln(l.norm3)
             _, h3 = ops.layernorm(x, g, b, e, want_bf16=True, split=True)
