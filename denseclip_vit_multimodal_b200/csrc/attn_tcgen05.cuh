@@ -461,7 +461,21 @@ struct SmallAttnParams {
   int causal;                  // 1: key j allowed iff j <= query index
   void* out; int out_f32; int ldo; long long out_bs;  // out[b][row][h*64 + d]
   int out_split_off;           // > 0 (bf16 out only): also write lo = bf16(v - hi) at this column offset
+  int key_splits;              // > 1: the keys are split over this many CTAs per (batch, head, query block); partial results
+  float* ws;                   //      (unnormalised O[64], running max, row sum per query) go to ws, attn_small_combine_kernel merges them
 };
+
+// one output element: fp32, or bf16 (+ optional lo half)
+__device__ __forceinline__ void attn_small_store(const SmallAttnParams& p, long long ooff, float o) {
+  if (p.out_f32) {
+    reinterpret_cast<float*>(p.out)[ooff] = o;
+  } else {
+    const __nv_bfloat16 hi = __float2bfloat16(o);
+    reinterpret_cast<__nv_bfloat16*>(p.out)[ooff] = hi;
+    if (p.out_split_off > 0)
+      reinterpret_cast<__nv_bfloat16*>(p.out)[ooff + p.out_split_off] = __float2bfloat16(o - __bfloat162float(hi));
+  }
+}
 
 __device__ __forceinline__ float ld_elem(const void* base, int is_f32, long long idx) {
   return is_f32 ? reinterpret_cast<const float*>(base)[idx] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
@@ -469,21 +483,27 @@ __device__ __forceinline__ float ld_elem(const void* base, int is_f32, long long
 
 // dynamic smem: QB*Nk floats (scores) + QB*64 (q) + 8*QB*64 (partial O) + 16*QB (reduction scratch).
 // QB = queries handled per CTA (they share every K/V load); a CTA covers queries [q0, q0 + QB) of one (batch, head).
-template <int QB>
+// DPT = output dims per thread in phase 2 (8, or 4 for the wide-QB variant whose accumulators would not fit otherwise).
+template <int QB, int DPT = (QB > 8 ? 4 : 8)>
 __global__ void __launch_bounds__(256) attn_small_kernel(const SmallAttnParams p) {
   extern __shared__ float sm[];
-  float* sc = sm;                       // [QB][Nk]
-  float* sq = sm + QB * p.Nk;           // [QB][64]
+  const int S = p.key_splits > 1 ? p.key_splits : 1;
+  const int span = (p.Nk + S - 1) / S;  // keys handled by one CTA
+  float* sc = sm;                       // [QB][span]
+  float* sq = sm + ((QB * span + 3) & ~3);  // [QB][64], 16-byte aligned (read as float4)
   float* so = sq + QB * 64;             // [8 warps][QB][64]
   float* red = so + 8 * QB * 64;        // [2][8][QB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nqb = (p.q_count + QB - 1) / QB;
-  const int q0 = p.q_first + (blockIdx.x % nqb) * QB;
-  const int h = (blockIdx.x / nqb) % p.H;
-  const int b = blockIdx.x / (nqb * p.H);
+  const int ks = blockIdx.x % S, bid = blockIdx.x / S;
+  const int q0 = p.q_first + (bid % nqb) * QB;
+  const int h = (bid / nqb) % p.H;
+  const int b = bid / (nqb * p.H);
   const int nq = min(QB, p.q_first + p.q_count - q0);
   // causal: query qi may see keys j <= qi; the CTA scans up to its last query's limit and masks per query
-  const int nk = p.causal ? min(p.Nk, q0 + nq) : p.Nk;
+  const int nk_all = p.causal ? min(p.Nk, q0 + nq) : p.Nk;
+  // key range of this CTA (the whole range unless the launch splits the keys); scores are stored relative to k0
+  const int k0 = ks * span, nk = min(nk_all, k0 + span);
   for (int i = tid; i < QB * 64; i += 256) {
     const int qq = i >> 6, d = i & 63;
     sq[i] = qq < nq ? ld_elem(p.q, p.is_f32, b * p.q_bs + (long long)(q0 + qq) * p.ldq + p.q_col0 + h * 64 + d) * p.scale : 0.f;
@@ -493,7 +513,7 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const SmallAttnParams p
   float mx[QB];
 #pragma unroll
   for (int qq = 0; qq < QB; ++qq) mx[qq] = -INFINITY;
-  for (int j = tid; j < nk; j += 256) {
+  for (int j = k0 + tid; j < nk; j += 256) {
     const long long koff = b * p.k_bs + (long long)j * p.ldk + p.k_col0 + h * 64;
     float kf[64];
     if (p.is_f32) {
@@ -519,14 +539,18 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const SmallAttnParams p
 #pragma unroll
     for (int qq = 0; qq < QB; ++qq) {
       float s0 = 0.f, s1 = 0.f;
+      const float4* q4 = reinterpret_cast<const float4*>(sq + qq * 64);  // broadcast 128-bit smem reads: 16 per query instead of 64
 #pragma unroll
-      for (int d = 0; d < 64; d += 2) {
-        s0 += sq[qq * 64 + d] * kf[d];
-        s1 += sq[qq * 64 + d + 1] * kf[d + 1];
+      for (int d = 0; d < 16; ++d) {
+        const float4 qv = q4[d];
+        s0 += qv.x * kf[4 * d];
+        s1 += qv.y * kf[4 * d + 1];
+        s0 += qv.z * kf[4 * d + 2];
+        s1 += qv.w * kf[4 * d + 3];
       }
       float s = s0 + s1;
       if (p.causal && j > q0 + qq) s = -INFINITY;
-      sc[qq * p.Nk + j] = s;
+      sc[qq * span + (j - k0)] = s;
       mx[qq] = fmaxf(mx[qq], s);
     }
   }
@@ -546,11 +570,11 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const SmallAttnParams p
     mx[qq] = m;
     sum[qq] = 0.f;
   }
-  for (int j = tid; j < nk; j += 256) {
+  for (int j = k0 + tid; j < nk; j += 256) {
 #pragma unroll
     for (int qq = 0; qq < QB; ++qq) {
-      const float e = __expf(sc[qq * p.Nk + j] - mx[qq]);
-      sc[qq * p.Nk + j] = e;
+      const float e = __expf(sc[qq * span + (j - k0)] - mx[qq]);
+      sc[qq * span + (j - k0)] = e;
       sum[qq] += e;
     }
   }
@@ -561,31 +585,41 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const SmallAttnParams p
     if (lane == 0) red[8 * QB + warp * QB + qq] = sum[qq];
   }
   __syncthreads();
-  // phase 2: O[q][d] = sum_j p[q][j] V[j][d]; thread (g, d8) covers keys j = g, g+32, ... and 8 consecutive dims
-  const int d8 = tid & 7, g = tid >> 3;
-  float acc[QB][8];
+  // phase 2: O[q][d] = sum_j p[q][j] V[j][d]; thread (g, dq) covers keys j = g, g + KG, ... and DPT consecutive dims
+  constexpr int TPR = 64 / DPT, KG = 256 / TPR;  // threads per V row, key groups
+  const int dq = tid % TPR, g = tid / TPR;
+  float acc[QB][DPT];
 #pragma unroll
   for (int qq = 0; qq < QB; ++qq)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[qq][e] = 0.f;
-  const long long vbase = b * p.v_bs + p.v_col0 + h * 64 + d8 * 8;
-  for (int j0 = g; j0 < nk; j0 += 64) {
-    float vf[2][8];
+    for (int e = 0; e < DPT; ++e) acc[qq][e] = 0.f;
+  const long long vbase = b * p.v_bs + p.v_col0 + h * 64 + dq * DPT;
+  for (int j0 = k0 + g; j0 < nk; j0 += 2 * KG) {
+    float vf[2][DPT];
     int jj[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const int j = j0 + 32 * u;
+      const int j = j0 + KG * u;
       jj[u] = j;
       const long long voff = vbase + (long long)(j < nk ? j : j0) * p.ldv;
       if (p.is_f32) {
         const float4* vp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.v) + voff);
-        const float4 a = vp[0], c = vp[1];
-        vf[u][0] = a.x; vf[u][1] = a.y; vf[u][2] = a.z; vf[u][3] = a.w; vf[u][4] = c.x; vf[u][5] = c.y; vf[u][6] = c.z; vf[u][7] = c.w;
-      } else {
-        const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.v) + voff);
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e4 = 0; e4 < DPT / 4; ++e4) {
+          const float4 a = vp[e4];
+          vf[u][4 * e4] = a.x; vf[u][4 * e4 + 1] = a.y; vf[u][4 * e4 + 2] = a.z; vf[u][4 * e4 + 3] = a.w;
+        }
+      } else {
+        uint32_t w[DPT / 2];
+        if constexpr (DPT == 8) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.v) + voff);
+          w[0] = raw.x; w[1] = raw.y; w[2] = raw.z; w[3] = raw.w;
+        } else {
+          const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.v) + voff);
+          w[0] = raw.x; w[1] = raw.y;
+        }
+#pragma unroll
+        for (int e = 0; e < DPT / 2; ++e) {
           vf[u][2 * e] = __uint_as_float(w[e] << 16);
           vf[u][2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
         }
@@ -596,9 +630,9 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const SmallAttnParams p
       if (jj[u] < nk) {
 #pragma unroll
         for (int qq = 0; qq < QB; ++qq) {
-          const float pj = sc[qq * p.Nk + jj[u]];
+          const float pj = sc[qq * span + (jj[u] - k0)];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[qq][e] += pj * vf[u][e];
+          for (int e = 0; e < DPT; ++e) acc[qq][e] += pj * vf[u][e];
         }
       }
     }
@@ -606,15 +640,15 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const SmallAttnParams p
 #pragma unroll
   for (int qq = 0; qq < QB; ++qq)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[qq][e] += __shfl_xor_sync(0xffffffffu, acc[qq][e], 8);
+    for (int e = 0; e < DPT; ++e) {
+      if constexpr (TPR == 8) acc[qq][e] += __shfl_xor_sync(0xffffffffu, acc[qq][e], 8);
       acc[qq][e] += __shfl_xor_sync(0xffffffffu, acc[qq][e], 16);
     }
-  if (lane < 8) {
+  if (lane < TPR) {
 #pragma unroll
     for (int qq = 0; qq < QB; ++qq)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) so[(warp * QB + qq) * 64 + lane * 8 + e] = acc[qq][e];
+      for (int e = 0; e < DPT; ++e) so[(warp * QB + qq) * 64 + lane * DPT + e] = acc[qq][e];
   }
   __syncthreads();
   for (int i = tid; i < nq * 64; i += 256) {
@@ -625,17 +659,52 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const SmallAttnParams p
       o += so[(w * QB + qq) * 64 + d];
       ssum += red[8 * QB + w * QB + qq];
     }
-    o /= ssum;
-    const long long ooff = b * p.out_bs + (long long)(q0 + qq) * p.ldo + h * 64 + d;
-    if (p.out_f32) {
-      reinterpret_cast<float*>(p.out)[ooff] = o;
+    if (S > 1) {  // partial result of this key range: [O (unnormalised) x 64 | max | sum] per query
+      float* w = p.ws + ((size_t(bid) * S + ks) * QB + qq) * 66;
+      w[d] = o;
+      if (d == 0) {
+        float m = red[qq];
+#pragma unroll
+        for (int ww = 1; ww < 8; ++ww) m = fmaxf(m, red[ww * QB + qq]);
+        w[64] = m;
+        w[65] = ssum;
+      }
     } else {
-      const __nv_bfloat16 hi = __float2bfloat16(o);
-      reinterpret_cast<__nv_bfloat16*>(p.out)[ooff] = hi;
-      if (p.out_split_off > 0)
-        reinterpret_cast<__nv_bfloat16*>(p.out)[ooff + p.out_split_off] = __float2bfloat16(o - __bfloat162float(hi));
+      attn_small_store(p, b * p.out_bs + (long long)(q0 + qq) * p.ldo + h * 64 + d, o / ssum);
     }
   }
+}
+
+// merges the key-range partials of attn_small_kernel: one 64-thread CTA per (batch, head, query block, query), thread = dim
+template <int QB>
+__global__ void __launch_bounds__(64) attn_small_combine_kernel(const SmallAttnParams p) {
+  const int nqb = (p.q_count + QB - 1) / QB, S = p.key_splits;
+  const int bid = blockIdx.x / QB, qq = blockIdx.x % QB, d = threadIdx.x;
+  const int q0 = p.q_first + (bid % nqb) * QB;
+  const int h = (bid / nqb) % p.H;
+  const int b = bid / (nqb * p.H);
+  if (q0 + qq >= p.q_first + p.q_count) return;
+  const float* w = p.ws + (size_t(bid) * S * QB + qq) * 66;
+  float ms[8], ls[8], os[8];  // S <= 8: all partials are fetched before any of them is used
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const bool on = s < S;
+    const float* wsp = w + size_t(on ? s : 0) * QB * 66;
+    ms[s] = on ? wsp[64] : -INFINITY;
+    ls[s] = on ? wsp[65] : 0.f;
+    os[s] = on ? wsp[d] : 0.f;
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) m = fmaxf(m, ls[s] > 0.f ? ms[s] : -INFINITY);
+  float num = 0.f, den = 0.f;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const float f = ls[s] > 0.f ? __expf(ms[s] - m) : 0.f;  // an empty key range contributes nothing
+    num += f * os[s];
+    den += f * ls[s];
+  }
+  attn_small_store(p, b * p.out_bs + (long long)(q0 + qq) * p.ldo + h * 64 + d, num / den);
 }
 
 }  // namespace dclip

@@ -19,6 +19,7 @@ struct dclip_handle_s {
   // plan caches: tensor maps are encoded once per distinct argument set
   std::map<std::string, GemmPlan> gemm_plans;
   std::map<std::string, AttnPlan> attn_plans;
+  AttnSmallScratch attn_small_scratch;  // key-split partials (one buffer per handle: calls on one handle must not overlap across streams)
 };
 
 struct dclip_vit_s {
@@ -88,6 +89,7 @@ int dclip_create(int device, dclip_handle_t* out) {
 }
 
 int dclip_destroy(dclip_handle_t h) {
+  if (h && h->attn_small_scratch.ptr) cudaFree(h->attn_small_scratch.ptr);
   delete h;
   return 0;
 }
@@ -187,8 +189,7 @@ int dclip_attention_small(dclip_handle_t h, const void* q, const void* k, const 
     const int align = is_f32 ? 4 : 8;
     DCLIP_REQUIRE(ldk % align == 0 && ldv % align == 0 && k_col0 % align == 0 && v_col0 % align == 0 && k_bs % align == 0 &&
                       v_bs % align == 0, "small attention: K/V rows must be 16B aligned");
-    run_attn_small(p, static_cast<cudaStream_t>(stream));
-    h->launches += 1;
+    h->launches += run_attn_small(p, static_cast<cudaStream_t>(stream), &h->attn_small_scratch);
   });
 }
 

@@ -403,25 +403,71 @@ inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
   }
 }
 
+// scratch for the key-split partials: grown on demand (dclip_api.cu keeps one buffer per handle)
+struct AttnSmallScratch {
+  float* ptr = nullptr;
+  size_t bytes = 0;
+};
+
 template <int QB>
-inline void launch_attn_small(const SmallAttnParams& p, cudaStream_t stream) {
-  const size_t smem = (size_t(QB) * p.Nk + QB * 64 + 8 * QB * 64 + 16 * QB) * 4;
+inline int launch_attn_small(SmallAttnParams p, cudaStream_t stream, AttnSmallScratch* scratch) {
+  const int nqb = (p.q_count + QB - 1) / QB;
+  const int ctas = p.B * p.H * nqb;
+  // long key ranges with few (batch, head, query-block) CTAs -- the ContextDecoder cross attention: 19 queries over 2048
+  // keys -- are split over the keys (flash-decoding style) so the K/V stream is spread over ~4 waves of CTAs
+  int S = 1;
+  static const bool no_split = [] { const char* e = getenv("DCLIP_ATTN_SMALL_NO_SPLIT"); return e && e[0] == '1'; }();
+  if (scratch && !no_split && !p.causal && p.Nk >= 1024) {
+    S = (4 * sm_count() + ctas / 2) / ctas;
+    S = S < 1 ? 1 : (S > 8 ? 8 : S);
+    while (S > 1 && (p.Nk + S - 1) / S < 256) --S;
+  }
+  if (S > 1) {
+    const size_t need = size_t(ctas) * S * QB * 66 * sizeof(float);
+    if (scratch->bytes < need) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      DCLIP_CHECK_CUDA(cudaStreamIsCapturing(stream, &cs));
+      DCLIP_REQUIRE(cs == cudaStreamCaptureStatusNone, "small attention: scratch must be sized by an eager warm-up call before graph capture");
+      if (scratch->ptr) DCLIP_CHECK_CUDA(cudaFree(scratch->ptr));
+      scratch->ptr = nullptr; scratch->bytes = 0;
+      DCLIP_CHECK_CUDA(cudaMalloc(&scratch->ptr, need));
+      scratch->bytes = need;
+    }
+    p.key_splits = S;
+    p.ws = scratch->ptr;
+  } else {
+    p.key_splits = 1;
+    p.ws = nullptr;
+  }
+  const int span = (p.Nk + S - 1) / S;
+  const size_t smem = (((size_t(QB) * span + 3) & ~size_t(3)) + QB * 64 + 8 * QB * 64 + 16 * QB) * 4;
+  if constexpr (QB > 8) {
+    if (smem > 200 * 1024) return launch_attn_small<8>(p, stream, scratch);  // (key splitting disabled: scores of 20 queries do not fit)
+  }
   DCLIP_REQUIRE(smem <= 200 * 1024, "small attention: Nk=%d too large for the smem score buffer", p.Nk);
   static bool attr = false;
   if (!attr) {
     DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  const int nqb = (p.q_count + QB - 1) / QB;
-  attn_small_kernel<QB><<<p.B * p.H * nqb, 256, smem, stream>>>(p);
+  attn_small_kernel<QB><<<ctas * S, 256, smem, stream>>>(p);
   DCLIP_CHECK_CUDA(cudaGetLastError());
+  if (S > 1) {
+    attn_small_combine_kernel<QB><<<ctas * QB, 64, 0, stream>>>(p);
+    DCLIP_CHECK_CUDA(cudaGetLastError());
+  }
+  return S > 1 ? 2 : 1;
 }
 
-inline void run_attn_small(const SmallAttnParams& p, cudaStream_t stream) {
+// returns the number of kernels launched
+inline int run_attn_small(const SmallAttnParams& p, cudaStream_t stream, AttnSmallScratch* scratch = nullptr) {
   DCLIP_REQUIRE(p.q_count > 0 && p.Nk > 0, "bad small-attention shape");
-  if (p.q_count == 1) launch_attn_small<1>(p, stream);
-  else if (p.q_count <= 4 || p.Nk > 4096) launch_attn_small<4>(p, stream);
-  else launch_attn_small<8>(p, stream);
+  if (p.q_count == 1) return launch_attn_small<1>(p, stream, scratch);
+  // 9..20 queries over a long key range (ContextDecoder cross attention: 19 class queries x 2048 visual tokens): one query
+  // block per (batch, head), so K and V are streamed once instead of once per 8 queries; the keys are split over CTAs
+  if (scratch && !p.causal && p.q_count > 8 && p.q_count <= 20 && p.Nk >= 1024) return launch_attn_small<20>(p, stream, scratch);
+  if (p.q_count <= 4 || p.Nk > 4096) return launch_attn_small<4>(p, stream, scratch);
+  return launch_attn_small<8>(p, stream, scratch);
 }
 
 }  // namespace dclip

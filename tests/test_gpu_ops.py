@@ -70,7 +70,8 @@ def test_flash_attention_vs_sdpa(ops, B, H, N):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("causal,Nq,Nk", [(False, 19, 19), (False, 19, 2049), (True, 22, 22), (False, 1, 300)])
+@pytest.mark.parametrize("causal,Nq,Nk", [(False, 19, 19), (False, 19, 2049), (True, 22, 22), (False, 1, 300), (False, 19, 1025),
+                                          (False, 5, 4100), (False, 1, 2049)])   # the long-key cases run key-split + combine
 def test_attention_small(ops, dtype, causal, Nq, Nk):
     B, H = 3, 4
     D = H * 64
@@ -88,6 +89,12 @@ def test_attention_small(ops, dtype, causal, Nq, Nk):
     vv = v[..., cols[2]:cols[2] + D].float().view(B, Nk, H, 64).transpose(1, 2)
     ref = F.scaled_dot_product_attention(qq, kk, vv, is_causal=causal).transpose(1, 2).reshape(B, Nq, D)
     assert rel_err(out, ref) < 2e-5
+    # hi|lo bf16 output written by the kernel == split of the fp32 result
+    out2 = torch.empty(B, Nq, 2 * D, dtype=torch.bfloat16, device="cuda")
+    ops.attention_small(q, k, v, B=B, H=H, q_first=0, q_count=Nq, Nk=Nk, q_col0=cols[0], k_col0=cols[1], v_col0=cols[2],
+                        scale=0.125, out=out2, causal=causal, out_split_off=D)
+    hi = out.bfloat16()
+    assert torch.equal(out2[..., :D], hi) and torch.equal(out2[..., D:], (out - hi.float()).bfloat16())
 
 
 @pytest.mark.parametrize("g0,gh,gw", [(14, 32, 64), (2, 2, 4), (14, 14, 14), (7, 3, 5)])
