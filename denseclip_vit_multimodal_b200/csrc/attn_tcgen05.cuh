@@ -32,6 +32,12 @@ struct AttnParams {
   long long out_batch_stride;  // elements
   int ldo;                     // elements
   int token_mode;              // 0: no MUFU token, 1: hand over after the exp phase, 2: hand over at 3/4 of it
+  // raw operand pointers (same tensors as the TMA maps): used by the CUDA-core path that serves a query block with only a
+  // few valid rows (the 2049th token of a 256-row blocking), see attn_tail_rows
+  const __nv_bfloat16 *q, *k, *v;
+  int ldq, ldk, ldv;
+  long long q_bs, k_bs, v_bs;
+  int tail_rows_max;           // query blocks with <= this many valid rows take the CUDA-core path (0 = never)
   long long* dbg;              // optional timeline buffer (selftest only): clock64 stamps of CTA `dbg_cta`
   int dbg_cta;
 };
@@ -106,7 +112,12 @@ __device__ __forceinline__ void exp2_poly_x2(uint64_t t2, float& p0, float& p1) 
 }
 
 // POLY = number of column pairs (of the 4 pairs in every group of 8 columns) whose exp2 runs on the FMA pipe
-template <int NC, bool PT, int POLY>
+// DEFER (P in TMEM only): P(j) may only be written once PV(j-1) has consumed P(j-1) (single P buffer), and that MMA is
+// issued ~300 cycles after this warpgroup published P(j-1) and completes ~600 cycles later -- on the critical chain of the
+// warpgroup if waited for before the exponentials.  With DEFER the packed bf16 probabilities of the first 3/4 of the tile
+// stay in registers (48), the PV-done barrier is probed at 1/2 and waited for at 3/4 of the exponential phase (by then
+// it has long completed), and the TMEM stores of the first three chunks overlap the last quarter's exponentials.
+template <int NC, bool PT, int POLY, bool DEFER = false>
 __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint32_t tP, uint8_t* sProw, int r, int lane, int valid,
                                                   bool first, float sc, float& m_used, float& l, uint64_t* s_free_bar,
                                                   uint64_t* o_done_bar, uint32_t o_done_parity, int wg, bool last_tile,
@@ -145,7 +156,8 @@ __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint
   }
   // PV of the previous tile must be done before P is overwritten or O is touched.  It was issued when this warpgroup
   // arrived on p_ready a whole load+max phase ago, so this wait normally returns at once.
-  if (!first) {
+  constexpr bool kDefer = DEFER && PT;
+  if (!first && (!kDefer || rescale)) {
     mbar_wait(o_done_bar, o_done_parity);
     tc_fence_after();
     if (rescale) {
@@ -161,7 +173,7 @@ __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint
       tmem_wait_st();
     }
   }
-  DCLIP_TL(if (dbg) dbg[4] = clock64();)
+  if (!kDefer) { DCLIP_TL(if (dbg) dbg[4] = clock64();) }
   // MUFU token: only one warpgroup at a time runs its exponential phase (the SFU pipe is the bottleneck at head_dim 64:
   // 128 ex2 per row per tile); the other one overlaps its TMEM loads / max / barrier work with it.
   if (token_mode) named_bar_sync(1 + wg, 256);
@@ -170,7 +182,10 @@ __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint
   const float nmc = -m_used * sc;
   const uint64_t nmc2 = pack_f32x2(nmc, nmc);
   uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
-  uint32_t pk[16];
+  uint32_t pk[kDefer ? NC / 2 : 16];
+  constexpr int WAIT_AT = NC == 128 ? 11 : NC / 8 - 1;  // 8-column group (of NC / 8) after which the deferred chunks are stored
+  constexpr int PROBE_AT = NC == 128 ? 6 : -1;
+  bool pv_done = false;
 #pragma unroll
   for (int c16 = 0; c16 < NC / 8; ++c16) {
     float pv[8];
@@ -188,7 +203,22 @@ __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint
     }
     acc0 = add_f32x2(acc0, add_f32x2(pack_f32x2(pv[0], pv[1]), pack_f32x2(pv[2], pv[3])));
     acc1 = add_f32x2(acc1, add_f32x2(pack_f32x2(pv[4], pv[5]), pack_f32x2(pv[6], pv[7])));
-    if constexpr (PT) {
+    if constexpr (kDefer) {
+      pk[c16 * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
+      pk[c16 * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+      pk[c16 * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
+      pk[c16 * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
+      if (c16 == PROBE_AT) pv_done = mbar_test_wait(o_done_bar, o_done_parity);  // parity of a fresh barrier's "previous" phase passes at j = 0
+      if (c16 == WAIT_AT) {
+        if (!pv_done) mbar_wait(o_done_bar, o_done_parity);
+        tc_fence_after();
+        DCLIP_TL(if (dbg) dbg[4] = clock64();)
+#pragma unroll
+        for (int ch = 0; ch <= WAIT_AT / 4; ++ch) tmem_st_32x32b_x16(tP + ch * 16, reinterpret_cast<uint32_t(&)[16]>(pk[ch * 16]));
+      } else if (c16 > WAIT_AT && (c16 & 3) == 3) {
+        tmem_st_32x32b_x16(tP + (c16 >> 2) * 16, reinterpret_cast<uint32_t(&)[16]>(pk[(c16 >> 2) * 16]));
+      }
+    } else if constexpr (PT) {
       // P stays on-chip in TMEM: lane = query row, 32-bit column c holds (P[2c], P[2c+1]) -- the A operand of the TS MMA
       pk[(c16 & 3) * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
       pk[(c16 & 3) * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
@@ -210,7 +240,268 @@ __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint
   DCLIP_TL(if (dbg) dbg[3] = clock64();)
 }
 
-template <bool PT, int POLY = 0>
+// Speculative-max variant of attn_softmax_tile for KV tiles j >= 1.  The serial chain of one warpgroup per tile
+// (barrier wait -> TMEM load -> row max -> PV-done wait -> exponentials -> publish) is longer than the SFU work of the two
+// warpgroups together, so the chain, not the SFU, sets the step time (profiles/r01_attention_notes.md).  Here the
+// exponentials run against the STALE reference maximum m_used straight after the load; the tile's row maximum is reduced
+// inside the same instruction stream (FMNMX3 in the shadow of the MUFU issue slots) and only checked afterwards.  The
+// lazy-rescale rule is unchanged (rescale when the maximum grew by more than 2^8), so the result is identical to the
+// classic order: in the rare case a rescale is due, O and l are rescaled and the tile's exponentials are redone (the
+// scores are still in registers).  The PV(j-1)-done round trip is issued right behind the TMEM loads and overlaps their
+// latency.
+// DEFER: as in attn_softmax_tile, but the scores stay live for the redo, so only the first half of the tile is held back.
+template <int NC, bool PT, int POLY, bool DEFER = false>
+__device__ __forceinline__ void attn_softmax_tile_spec(uint32_t tS, uint32_t tO, uint32_t tP, uint8_t* sProw, int r, int lane,
+                                                       int valid, float sc, float& m_used, float& l, uint64_t* s_free_bar,
+                                                       uint64_t* o_done_bar, uint32_t o_done_parity, int wg, bool last_tile,
+                                                       int token_mode, long long* dbg) {
+  uint32_t su[NC];
+#pragma unroll
+  for (int c = 0; c < NC / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, reinterpret_cast<uint32_t(&)[32]>(su[c * 32]));
+  constexpr bool kDefer = DEFER && PT;
+  if constexpr (!kDefer) {
+    mbar_wait(o_done_bar, o_done_parity);  // P (and O) are free again; ~120-cycle round trip hidden behind the loads
+    tc_fence_after();
+    DCLIP_TL(if (dbg) dbg[4] = clock64();)
+  }
+  tmem_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(s_free_bar);
+  DCLIP_TL(if (dbg) dbg[1] = clock64();)
+  if (valid < NC) {
+#pragma unroll
+    for (int e = 0; e < NC; ++e)
+      if (e >= valid) su[e] = 0xff800000u;  // -inf
+  }
+  DCLIP_TL(if (dbg) dbg[2] = clock64();)
+  if (token_mode) named_bar_sync(1 + wg, 256);
+  const uint64_t sc2 = pack_f32x2(sc, sc);
+  uint64_t acc0, acc1;
+#pragma unroll 1
+  for (int pass = 0;; ++pass) {
+    const float nmc = -m_used * sc;
+    const uint64_t nmc2 = pack_f32x2(nmc, nmc);
+    acc0 = pack_f32x2(0.f, 0.f);
+    acc1 = acc0;
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+    uint32_t pk[kDefer ? NC / 2 : 16];
+    constexpr int WAIT_AT = NC == 128 ? 7 : NC / 8 - 1;
+    constexpr int PROBE_AT = NC == 128 ? 3 : -1;
+    bool pv_done = pass != 0;
+#pragma unroll
+    for (int c16 = 0; c16 < NC / 8; ++c16) {
+      float pv[8];
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        const uint64_t t = fma_f32x2(pack_f32x2(__uint_as_float(su[c16 * 8 + e]), __uint_as_float(su[c16 * 8 + e + 1])), sc2, nmc2);
+        if (e >= 8 - 2 * POLY) {
+          exp2_poly_x2(t, pv[e], pv[e + 1]);
+        } else {
+          float t0, t1;
+          unpack_f32x2(t, t0, t1);
+          pv[e] = ex2_approx(t0);
+          pv[e + 1] = ex2_approx(t1);
+        }
+      }
+      mx0 = fmaxf(mx0, fmaxf(__uint_as_float(su[c16 * 8 + 0]), __uint_as_float(su[c16 * 8 + 1])));
+      mx1 = fmaxf(mx1, fmaxf(__uint_as_float(su[c16 * 8 + 2]), __uint_as_float(su[c16 * 8 + 3])));
+      mx2 = fmaxf(mx2, fmaxf(__uint_as_float(su[c16 * 8 + 4]), __uint_as_float(su[c16 * 8 + 5])));
+      mx3 = fmaxf(mx3, fmaxf(__uint_as_float(su[c16 * 8 + 6]), __uint_as_float(su[c16 * 8 + 7])));
+      acc0 = add_f32x2(acc0, add_f32x2(pack_f32x2(pv[0], pv[1]), pack_f32x2(pv[2], pv[3])));
+      acc1 = add_f32x2(acc1, add_f32x2(pack_f32x2(pv[4], pv[5]), pack_f32x2(pv[6], pv[7])));
+      if constexpr (kDefer) {
+        pk[c16 * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
+        pk[c16 * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+        pk[c16 * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
+        pk[c16 * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
+        if (c16 == PROBE_AT && !pv_done) pv_done = mbar_test_wait(o_done_bar, o_done_parity);
+        if (c16 == WAIT_AT) {
+          if (!pv_done) mbar_wait(o_done_bar, o_done_parity);
+          tc_fence_after();
+          DCLIP_TL(if (dbg && !pass) dbg[4] = clock64();)
+#pragma unroll
+          for (int ch = 0; ch <= WAIT_AT / 4; ++ch) tmem_st_32x32b_x16(tP + ch * 16, reinterpret_cast<uint32_t(&)[16]>(pk[ch * 16]));
+        } else if (c16 > WAIT_AT && (c16 & 3) == 3) {
+          tmem_st_32x32b_x16(tP + (c16 >> 2) * 16, reinterpret_cast<uint32_t(&)[16]>(pk[(c16 >> 2) * 16]));
+        }
+      } else if constexpr (PT) {
+        pk[(c16 & 3) * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
+        pk[(c16 & 3) * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+        pk[(c16 & 3) * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
+        pk[(c16 & 3) * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
+        if ((c16 & 3) == 3) tmem_st_32x32b_x16(tP + (c16 >> 2) * 16, pk);
+      } else {
+        *reinterpret_cast<uint4*>(sProw + (c16 >> 3) * 16384 + (((c16 & 7) ^ (r & 7)) << 4)) =
+            make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+      }
+    }
+    if (pass) break;
+    const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+    const bool need = (m_new - m_used) * sc > 8.0f;
+    if (!__any_sync(0xffffffffu, need)) break;
+    // rare: the reference maximum moved by more than 2^8 -- rescale O and l, redo this tile's exponentials
+    const float alpha = ex2_approx((m_used - m_new) * sc);
+    m_used = m_new;
+    l *= alpha;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tO + c * 32, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+      tmem_st_32x32b_x32(tO + c * 32, o);
+    }
+    tmem_wait_st();
+  }
+  if (token_mode && (!last_tile || wg == 0)) named_bar_arrive(2 - wg, 256);
+  float a0, a1, a2, a3;
+  unpack_f32x2(acc0, a0, a1);
+  unpack_f32x2(acc1, a2, a3);
+  l += (a0 + a1) + (a2 + a3);
+  DCLIP_TL(if (dbg) dbg[3] = clock64();)
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CUDA-core path for a query block that holds only a few valid rows (N = 2049 tokens = 8 x 256 + 1: without it the ninth
+// CTA of every (image, head) would sweep all keys on the tensor cores for a single row, 11% of the grid).  The whole CTA
+// (384 threads) serves one query row at a time: thread-per-key dot products -> fp32 scores in shared memory -> block
+// softmax -> key-group-parallel PV with a shared-memory reduction.  Runs before any barrier / TMEM set-up.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float attn_block_reduce(float v, bool is_max, float* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, w) : v + w;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();  // s_red reuse
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  float r = s_red[0];
+  for (int w = 1; w < nw; ++w) r = is_max ? fmaxf(r, s_red[w]) : r + s_red[w];
+  return r;
+}
+
+struct AttnTailArgs {  // by-value subset of AttnParams, pre-offset to (image, head) -- keeps the kernel parameters out of local memory
+  const __nv_bfloat16 *q, *k, *v;
+  __nv_bfloat16* out;
+  int ldq, ldk, ldv, ldo, Nk;
+  float scale_log2;
+};
+
+__device__ __noinline__ void attn_tail_rows(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out,
+                                            int ldq, int ldk, int ldv, int ldo, int Nk, float scale_log2, int row0, int nrows,
+                                            uint8_t* smem) {
+  const AttnTailArgs p{q, k, v, out, ldq, ldk, ldv, ldo, Nk, scale_log2};
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int KG = nthr / 8;                                   // key groups of the PV phase (48)
+  float* s_part = reinterpret_cast<float*>(smem);            // [KG][64] partial outputs
+  float* s_red = s_part + KG * 64;                           // [32]
+  float* s_sc = s_red + 32;                                  // [Nk] scores / probabilities
+  const __nv_bfloat16* kb = p.k;
+  const __nv_bfloat16* vb = p.v;
+  for (int rr = 0; rr < nrows; ++rr) {
+    const int row = row0 + rr;
+    // 8 threads per key row (16 B each): a warp instruction touches 4 whole 128 B lines
+    const int g = tid >> 3, dq = tid & 7;
+    float qf[8];
+    {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(p.q + (long long)row * p.ldq) + dq);
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        qf[2 * e] = __uint_as_float(ww[e] << 16) * p.scale_log2;
+        qf[2 * e + 1] = __uint_as_float(ww[e] & 0xffff0000u) * p.scale_log2;
+      }
+    }
+    float lmax = -INFINITY;
+    const int trips = (p.Nk + KG - 1) / KG;  // warp-uniform trip count: the shuffles below need the whole warp
+    constexpr int NB = 16;  // independent 16 B loads in flight per thread before the first use
+    for (int t0 = 0; t0 < trips; t0 += NB) {
+      uint4 w[NB];
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int j = g + (t0 + u) * KG;
+        w[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (j < p.Nk) w[u] = __ldg(reinterpret_cast<const uint4*>(kb + (long long)j * p.ldk) + dq);
+      }
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int j = g + (t0 + u) * KG;
+        const uint32_t ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s0 = fmaf(qf[2 * e], __uint_as_float(ww[e] << 16), s0);
+          s1 = fmaf(qf[2 * e + 1], __uint_as_float(ww[e] & 0xffff0000u), s1);
+        }
+        float sj = s0 + s1;
+        sj += __shfl_xor_sync(0xffffffffu, sj, 1);
+        sj += __shfl_xor_sync(0xffffffffu, sj, 2);
+        sj += __shfl_xor_sync(0xffffffffu, sj, 4);
+        if (j < p.Nk) {
+          if (dq == 0) s_sc[j] = sj;
+          lmax = fmaxf(lmax, sj);
+        }
+      }
+    }
+    const float m = attn_block_reduce(lmax, true, s_red);
+    // (the reduction's barriers also publish s_sc)  P = exp2(s - m) is evaluated by all 8 threads of a key row; the row
+    // sum counts it once
+    float lsum = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int t0 = 0; t0 < trips; t0 += NB) {
+      uint4 w[NB];
+      float pj[NB];
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int j = g + (t0 + u) * KG;
+        w[u] = make_uint4(0u, 0u, 0u, 0u);
+        pj[u] = -INFINITY;
+        if (j < p.Nk) {
+          w[u] = __ldg(reinterpret_cast<const uint4*>(vb + (long long)j * p.ldv) + dq);
+          pj[u] = s_sc[j];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const float pu = ex2_approx(pj[u] - m);
+        lsum += pu;
+        const uint32_t ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] = fmaf(pu, __uint_as_float(ww[e] << 16), acc[2 * e]);
+          acc[2 * e + 1] = fmaf(pu, __uint_as_float(ww[e] & 0xffff0000u), acc[2 * e + 1]);
+        }
+      }
+    }
+    const float l = attn_block_reduce(dq == 0 ? lsum : 0.f, false, s_red);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_part[g * 64 + dq * 8 + e] = acc[e];
+    __syncthreads();
+    {  // two-level sum over the key groups: nthr / 64 slices first
+      const int d = tid & 63, slice = tid >> 6, nslice = nthr >> 6;
+      float o = 0.f;
+      for (int gg = slice; gg < KG; gg += nslice) o += s_part[gg * 64 + d];
+      __syncthreads();
+      s_part[slice * 64 + d] = o;
+      __syncthreads();
+      if (tid < 64) {
+        o = 0.f;
+        for (int sl = 0; sl < nslice; ++sl) o += s_part[sl * 64 + tid];
+        p.out[(long long)row * p.ldo + tid] = __float2bfloat16(o / l);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// MODE bit 0: speculative-max tiles for j >= 1 (attn_softmax_tile_spec); bit 1: deferred P stores (DEFER)
+template <bool PT, int POLY = 0, int MODE = 0>
 __global__ void __launch_bounds__(AttnCfgT<PT>::THREADS, 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -237,6 +528,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int last_valid = p.Nk - (T - 1) * Cfg::TKV;     // valid columns of the last KV tile (1..128)
   const int last_cols16 = (last_valid + 15) & ~15;      // MMA extent of the last KV tile
 
+  if (p.Nq_total - q_row0 <= p.tail_rows_max) {  // CTA-uniform: a block with a handful of valid rows skips the tensor-core machinery
+    attn_tail_rows(p.q + (long long)b * p.q_bs + p.q_col0 + h * 64, p.k + (long long)b * p.k_bs + p.k_col0 + h * 64,
+                   p.v + (long long)b * p.v_bs + p.v_col0 + h * 64, p.out + (long long)b * p.out_batch_stride + h * 64, p.ldq, p.ldk,
+                   p.ldv, p.ldo, p.Nk, p.scale_log2, q_row0, p.Nq_total - q_row0, smem);
+    return;
+  }
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) {
       printf("dclip attn: dynamic smem base not 1024B aligned\n");
@@ -400,10 +697,16 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       long long* dbg = nullptr;
       DCLIP_TL(dbg = (p.dbg && blockIdx.x == p.dbg_cta && (warp & 3) == 0 && lane == 0) ? p.dbg + (i * 32 + j) * 8 : nullptr;)
       DCLIP_TL(if (dbg) dbg[0] = clock64();)
-      if (valid > 32)
-        attn_softmax_tile<128, PT, POLY>(tS, tO, tP, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
+      constexpr bool SPEC = (MODE & 1) != 0, DEFER = (MODE & 2) != 0;
+      if (SPEC && j > 0) {
+        if (valid > 32)
+          attn_softmax_tile_spec<128, PT, POLY, DEFER>(tS, tO, tP, sProw, r, lane, valid, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
+        else
+          attn_softmax_tile_spec<32, PT, POLY, DEFER>(tS, tO, tP, sProw, r, lane, valid, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
+      } else if (valid > 32)
+        attn_softmax_tile<128, PT, POLY, DEFER>(tS, tO, tP, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
       else
-        attn_softmax_tile<32, PT, POLY>(tS, tO, tP, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
+        attn_softmax_tile<32, PT, POLY, DEFER>(tS, tO, tP, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
       if constexpr (PT) tmem_wait_st(); else fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();

@@ -367,6 +367,14 @@ inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
   plan.p = p;
   static const int token_env = [] { const char* e = getenv("DCLIP_ATTN_TOKEN"); return e ? atoi(e) : 1; }();
   plan.p.token_mode = token_env;
+  static const int tail_env = [] { const char* e = getenv("DCLIP_ATTN_TAIL_ROWS"); return e ? atoi(e) : 4; }();
+  plan.p.q = op.q; plan.p.k = op.k; plan.p.v = op.v;
+  plan.p.ldq = op.ldq; plan.p.ldk = op.ldk; plan.p.ldv = op.ldv;
+  plan.p.q_bs = op.q_bs; plan.p.k_bs = op.k_bs; plan.p.v_bs = op.v_bs;
+  // the CUDA-core tail path keeps one fp32 score per key in shared memory
+  plan.p.tail_rows_max = (size_t(p.Nk) * 4 + 16384 <= size_t(AttnCfg::SMEM_BYTES)) ? tail_env : 0;
+  DCLIP_REQUIRE(op.ldq % 8 == 0 && op.ldk % 8 == 0 && op.ldv % 8 == 0 && p.q_col0 % 8 == 0 && p.k_col0 % 8 == 0 && p.v_col0 % 8 == 0 &&
+                op.q_bs % 8 == 0 && op.k_bs % 8 == 0 && op.v_bs % 8 == 0, "attention operand alignment");
   plan.tmQ = make_tmap_tokens_bf16(op.q, p.B, op.Nq_total, op.ldq, op.q_bs);
   plan.tmK = make_tmap_tokens_bf16(op.k, p.B, p.Nk, op.ldk, op.k_bs);
   plan.tmV = make_tmap_tokens_bf16(op.v, p.B, p.Nk, op.ldv, op.v_bs);
@@ -375,15 +383,15 @@ inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
   return plan;
 }
 
-template <bool PT, int POLY>
+template <bool PT, int POLY, int MODE>
 inline void run_attn_variant(const AttnPlan& plan, cudaStream_t stream) {
   using Cfg = AttnCfgT<PT>;
   static bool attr_set = false;
   if (!attr_set) {
-    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<PT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<PT, POLY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  attn_fwd_tcgen05_kernel<PT, POLY><<<plan.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.p);
+  attn_fwd_tcgen05_kernel<PT, POLY, MODE><<<plan.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.p);
   DCLIP_CHECK_CUDA(cudaGetLastError());
 }
 
@@ -392,14 +400,27 @@ inline void run_attn_variant(const AttnPlan& plan, cudaStream_t stream) {
 #ifndef DCLIP_ATTN_POLY_DEFAULT
 #define DCLIP_ATTN_POLY_DEFAULT 0
 #endif
+#ifndef DCLIP_ATTN_SPEC_DEFAULT
+#define DCLIP_ATTN_SPEC_DEFAULT 0  // speculative-max softmax tiles (measured slower with the MUFU token: 0.366 vs 0.349 ms)
+#endif
+#ifndef DCLIP_ATTN_DEFER_DEFAULT
+#define DCLIP_ATTN_DEFER_DEFAULT 0  // deferred P stores (measured slower: 0.373 vs 0.349 ms, profiles/r01_attention_notes.md)
+#endif
 inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
   static const bool p_smem = [] { const char* e = getenv("DCLIP_ATTN_P_SMEM"); return e && e[0] == '1'; }();
   static const int poly = [] { const char* e = getenv("DCLIP_ATTN_POLY"); return e ? atoi(e) : DCLIP_ATTN_POLY_DEFAULT; }();
-  if (p_smem) return run_attn_variant<false, 0>(plan, stream);
-  switch (poly) {
-    case 0: return run_attn_variant<true, 0>(plan, stream);
-    case 2: return run_attn_variant<true, 2>(plan, stream);
-    default: return run_attn_variant<true, 1>(plan, stream);
+  static const int spec = [] { const char* e = getenv("DCLIP_ATTN_SPEC"); return e ? atoi(e) : DCLIP_ATTN_SPEC_DEFAULT; }();
+  static const int defer = [] { const char* e = getenv("DCLIP_ATTN_DEFER"); return e ? atoi(e) : DCLIP_ATTN_DEFER_DEFAULT; }();
+  if (p_smem) return run_attn_variant<false, 0, 0>(plan, stream);
+  switch ((poly ? 4 : 0) | (defer ? 2 : 0) | (spec ? 1 : 0)) {
+    case 0: return run_attn_variant<true, 0, 0>(plan, stream);
+    case 1: return run_attn_variant<true, 0, 1>(plan, stream);
+    case 2: return run_attn_variant<true, 0, 2>(plan, stream);
+    case 3: return run_attn_variant<true, 0, 3>(plan, stream);
+    case 4: return run_attn_variant<true, 1, 0>(plan, stream);
+    case 5: return run_attn_variant<true, 1, 1>(plan, stream);
+    case 6: return run_attn_variant<true, 1, 2>(plan, stream);
+    default: return run_attn_variant<true, 1, 3>(plan, stream);
   }
 }
 

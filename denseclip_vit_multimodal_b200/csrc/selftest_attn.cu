@@ -155,6 +155,33 @@ int main(int argc, char** argv) {
     }
     return 0;
   }
+  if (argc > 5 && !strcmp(argv[1], "qstart")) {  // time the launch restricted to query rows >= q_start (no check)
+    const int B = atoi(argv[2]), H = atoi(argv[3]), N = atoi(argv[4]), qs = atoi(argv[5]);
+    const int D = H * 64, ld = 3 * D;
+    __nv_bfloat16 *qkv, *out;
+    cudaMalloc(&qkv, size_t(B) * N * ld * 2); cudaMalloc(&out, size_t(B) * N * D * 2);
+    fill_bf16<<<(size_t(B) * N * ld + 255) / 256, 256>>>(qkv, size_t(B) * N * ld, 11u, 2.0f);
+    AttnOperands op{qkv, qkv, qkv, ld, ld, ld, (long long)N * ld, (long long)N * ld, (long long)N * ld, N};
+    AttnParams p{};
+    p.B = B; p.H = H; p.Nq_total = N; p.q_start = qs; p.Nk = N; p.q_col0 = 0; p.k_col0 = D; p.v_col0 = 2 * D;
+    p.scale_log2 = 0.125f * 1.4426950408889634f; p.out = out; p.out_batch_stride = (long long)N * D; p.ldo = D;
+    AttnPlan plan = make_attn_plan(op, p);
+    for (int i = 0; i < 3; ++i) run_attn(plan, 0);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    for (int i = 0; i < 20; ++i) run_attn(plan, 0);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("q_start=%d grid=%d time=%.4f ms per launch (%s)\n", qs, plan.grid, ms / 20, cudaGetErrorString(cudaGetLastError()));
+    return 0;
+  }
+  if (argc > 4 && !strcmp(argv[1], "prof2")) {  // production blocking (q_start = 0), timing only
+    run_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), 2.0f, false, true);
+    return g_fail ? 1 : 0;
+  }
   if (argc > 4 && !strcmp(argv[1], "prof")) {
     run_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), 2.0f, true, true);
     return g_fail ? 1 : 0;

@@ -58,7 +58,9 @@ def test_layernorm(ops, M, D):
     assert rel_err(ob[:, :D].float() + ob[:, D:].float(), ref) < 2e-5
 
 
-@pytest.mark.parametrize("B,H,N", [(1, 1, 1), (2, 2, 129), (1, 4, 1025), (2, 12, 2049), (1, 2, 2629)])
+# N % 256 in 1..4: the last query block takes the kernel's CUDA-core tail path (attn_tail_rows); 5: tensor-core path again
+@pytest.mark.parametrize("B,H,N", [(1, 1, 1), (2, 2, 129), (1, 4, 1025), (2, 12, 2049), (1, 2, 2629), (2, 3, 260), (1, 2, 261),
+                                   (1, 2, 515)])
 def test_flash_attention_vs_sdpa(ops, B, H, N):
     D = H * 64
     qkv = _rand(B, N, 3 * D, scale=1.5, seed=11).bfloat16()
@@ -67,6 +69,9 @@ def test_flash_attention_vs_sdpa(ops, B, H, N):
     q, k, v = (t.float().view(B, N, H, 64).transpose(1, 2) for t in qkv.split(D, dim=-1))
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, D)
     assert rel_err(out, ref) < 1.5e-2
+    tail = N % 256
+    if tail:  # the rows of the ragged last block on their own (they are few: a global max would hide them)
+        assert rel_err(out[:, N - tail:], ref[:, N - tail:]) < 1.5e-2
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
