@@ -38,6 +38,8 @@ struct AttnParams {
   int ldq, ldk, ldv;
   long long q_bs, k_bs, v_bs;
   int tail_rows_max;           // query blocks with <= this many valid rows take the CUDA-core path (0 = never)
+  int peel_key0;               // 1: key 0 is handled on CUDA cores (score in the prologue, P*V in the output pass) and the KV tiles
+                               //    cover keys 1..Nk-1 -- for Nk = 128 t + 1 (2049 tokens) this saves the whole ragged last tile
   long long* dbg;              // optional timeline buffer (selftest only): clock64 stamps of CTA `dbg_cta`
   int dbg_cta;
 };
@@ -500,11 +502,45 @@ __device__ __noinline__ void attn_tail_rows(const __nv_bfloat16* q, const __nv_b
   }
 }
 
+
+// Output pass of one query tile: O (TMEM) * alpha + p0 * v_0 -> bf16 -> the thread's own row of the (finished) Q tile in
+// shared memory (same SWIZZLE_128B layout the TMA load produced) -> ONE TMA store per warpgroup.  The direct version
+// (each thread storing its 128-byte row with 16-byte st.global) cost ~4500 cycles per CTA: every warp instruction
+// touched 32 different lines, 4096 LSU wavefronts per CTA.  Rows beyond the tensor are clipped by the TMA unit.
+__device__ __forceinline__ void attn_store_tile(uint32_t tO, uint8_t* q_tile, int r, float alpha, float p0, bool fold,
+                                                const uint4 (&v0r)[8]) {
+  uint8_t* srow = q_tile + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t o[32];
+    tmem_ld_32x32b_x32(tO + c * 32, o);
+    tmem_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 32; e += 8) {
+      float f[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(o[e + u]) * alpha;
+      if (fold) {
+        const uint4 vv = v0r[c * 4 + (e >> 3)];
+        const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          f[2 * u] = fmaf(p0, __uint_as_float(vw[u] << 16), f[2 * u]);
+          f[2 * u + 1] = fmaf(p0, __uint_as_float(vw[u] & 0xffff0000u), f[2 * u + 1]);
+        }
+      }
+      *reinterpret_cast<uint4*>(srow + (((c * 4 + (e >> 3)) ^ (r & 7)) << 4)) =
+          make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+  }
+  fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy)
+}
+
 // MODE bit 0: speculative-max tiles for j >= 1 (attn_softmax_tile_spec); bit 1: deferred P stores (DEFER)
 template <bool PT, int POLY = 0, int MODE = 0>
 __global__ void __launch_bounds__(AttnCfgT<PT>::THREADS, 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                        const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
   using Cfg = AttnCfgT<PT>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
@@ -524,8 +560,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int h = (blockIdx.x / nqb) % p.H;
   const int b = blockIdx.x / (nqb * p.H);
   const int q_row0 = p.q_start + qb * 2 * Cfg::TQ;
-  const int T = (p.Nk + Cfg::TKV - 1) / Cfg::TKV;
-  const int last_valid = p.Nk - (T - 1) * Cfg::TKV;     // valid columns of the last KV tile (1..128)
+  const int koff = p.peel_key0 ? 1 : 0;                // first key of the tensor-core tiles
+  const int nk_eff = p.Nk - koff;
+  const int T = (nk_eff + Cfg::TKV - 1) / Cfg::TKV;
+  const int last_valid = nk_eff - (T - 1) * Cfg::TKV;   // valid columns of the last KV tile (1..128)
   const int last_cols16 = (last_valid + 15) & ~15;      // MMA extent of the last KV tile
 
   if (p.Nq_total - q_row0 <= p.tail_rows_max) {  // CTA-uniform: a block with a handful of valid rows skips the tensor-core machinery
@@ -581,9 +619,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           const uint32_t ph = (j / Cfg::KV_STAGES) & 1;
           mbar_wait(&kv_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&k_full[s], 16384);
-          tma_load_3d(smem + Cfg::K_OFF + s * 16384, &tmK, &k_full[s], p.k_col0 + h * Cfg::HD, j * Cfg::TKV, b);
+          tma_load_3d(smem + Cfg::K_OFF + s * 16384, &tmK, &k_full[s], p.k_col0 + h * Cfg::HD, koff + j * Cfg::TKV, b);
           mbar_arrive_expect_tx(&v_full[s], 16384);
-          tma_load_3d(smem + Cfg::V_OFF + s * 16384, &tmV, &v_full[s], p.v_col0 + h * Cfg::HD, j * Cfg::TKV, b);
+          tma_load_3d(smem + Cfg::V_OFF + s * 16384, &tmV, &v_full[s], p.v_col0 + h * Cfg::HD, koff + j * Cfg::TKV, b);
         }
       }
     } else if (warp == 8) {
@@ -688,6 +726,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const float sc = p.scale_log2;
     float m_used = -INFINITY, l = 0.f;
     if (i == 1 && p.token_mode) named_bar_arrive(1, 256);  // WG0 owns the MUFU token first
+    // peeled key 0 (koff): its score and its P*V term are computed on CUDA cores in the output pass; here only park the
+    // two 128 B lines (k_0, v_0 of this head) in L1 -- the K/V stream goes through TMA and never touches L1
+    if (koff && lane == 0) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.k + (long long)b * p.k_bs + p.k_col0 + h * Cfg::HD));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.v + (long long)b * p.v_bs + p.v_col0 + h * Cfg::HD));
+    }
 
     for (int j = 0; j < T; ++j) {
       DCLIP_TL(if (p.dbg && blockIdx.x == p.dbg_cta && (warp & 3) == 0 && lane == 0) p.dbg[(i * 32 + j) * 8 + 6] = clock64();)
@@ -715,27 +759,391 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
 
     // ------------------------------- output ---------------------------------------
-    mbar_wait(&o_done[i], (T - 1) & 1);
-    tc_fence_after();
-    const float inv = 1.0f / l;
-    const int row = q_row0 + i * Cfg::TQ + r;
-    __nv_bfloat16* orow = p.out + (long long)b * p.out_batch_stride + (long long)row * p.ldo + h * Cfg::HD;
+    // peeled key: z0 = scale_log2 * (q_r . k_0) from the Q row still sitting in the swizzled smem tile and k_0 from L1;
+    // everything is issued before the PV-done wait so it overlaps the last MMA
+    float z0 = 0.f;
+    uint4 v0r[8];
+    if (koff) {
+      const uint4* k0 = reinterpret_cast<const uint4*>(p.k + (long long)b * p.k_bs + p.k_col0 + h * Cfg::HD);
+      const uint4* v0 = reinterpret_cast<const uint4*>(p.v + (long long)b * p.v_bs + p.v_col0 + h * Cfg::HD);
+      const uint8_t* qrow = smem + Cfg::Q_OFF + i * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(tO + c * 32, o);
-      tmem_wait_ld();
-      if (row < p.Nq_total) {
+      for (int c = 0; c < 8; ++c) {
+        const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4));
+        const uint4 kv = __ldg(k0 + c);
+        v0r[c] = __ldg(v0 + c);
+        const uint32_t qq[4] = {qv.x, qv.y, qv.z, qv.w}, kk[4] = {kv.x, kv.y, kv.z, kv.w};
 #pragma unroll
-        for (int e = 0; e < 32; e += 8) {
-          const uint4 pk = make_uint4(pack_bf16x2(__uint_as_float(o[e]) * inv, __uint_as_float(o[e + 1]) * inv),
-                                      pack_bf16x2(__uint_as_float(o[e + 2]) * inv, __uint_as_float(o[e + 3]) * inv),
-                                      pack_bf16x2(__uint_as_float(o[e + 4]) * inv, __uint_as_float(o[e + 5]) * inv),
-                                      pack_bf16x2(__uint_as_float(o[e + 6]) * inv, __uint_as_float(o[e + 7]) * inv));
-          *reinterpret_cast<uint4*>(orow + c * 32 + e) = pk;
+        for (int e = 0; e < 4; ++e) {
+          s0 = fmaf(__uint_as_float(qq[e] << 16), __uint_as_float(kk[e] << 16), s0);
+          s1 = fmaf(__uint_as_float(qq[e] & 0xffff0000u), __uint_as_float(kk[e] & 0xffff0000u), s1);
         }
       }
+      z0 = (s0 + s1) * sc;
     }
+    mbar_wait(&o_done[i], (T - 1) & 1);
+    tc_fence_after();
+    // fold the peeled key in: renormalise to max(m_used, z0) so nothing can overflow
+    float alpha = 1.0f, p0 = 0.f;
+    if (koff) {
+      const float e0 = z0 - m_used * sc;
+      alpha = e0 > 0.f ? ex2_approx(-e0) : 1.0f;
+      p0 = e0 > 0.f ? 1.0f : ex2_approx(e0);
+      l = l * alpha + p0;
+    }
+    const float inv = 1.0f / l;
+    alpha *= inv;
+    p0 *= inv;
+    // this query tile's smem (all QK^T that read it are complete) stages the bf16 output for one TMA store per warpgroup
+    uint8_t* q_tile = smem + Cfg::Q_OFF + i * 16384;
+    attn_store_tile(tO, q_tile, r, alpha, p0, koff != 0, v0r);
+    named_bar_sync(3 + i, 128);
+    if (q == 0 && lane == 0) {
+      tma_store_3d(&tmO, q_tile, h * Cfg::HD, q_row0 + i * Cfg::TQ, b);
+      tma_store_commit();
+      tma_store_wait_read();  // the CTA (and its shared memory) may go away once every thread is through
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks a static list of (image, head, 256-query block) items.  Per item the
+// non-persistent kernel spends ~18% of its ~30 us outside the steady-state KV loop (CTA launch, barrier / TMEM set-up,
+// cold Q/K loads, first tiles without overlap, output pass with idle tensor cores).  Here TMEM, barriers and the K/V
+// ring live across items: the producer streams the next item's Q (double-buffered) and K/V tiles while the current item
+// finishes, the MMA warp issues the next item's first two QK^T as soon as the S buffers are free, and the softmax
+// warpgroups' output pass overlaps them.  All barrier parities run on a per-CTA global tile counter g = item * T + j.
+// Items whose block holds <= tail_rows_max valid rows are served first (CUDA-core path), before the pipeline exists.
+// ---------------------------------------------------------------------------------------------------------
+struct AttnPersistCfg {
+  static constexpr int TQ = 128, TKV = 128, HD = 64, KV_STAGES = 5;
+  static constexpr int Q_OFF = 0;                               // 2 buffers x 2 tiles x 16 KB
+  static constexpr int K_OFF = 4 * 16384;
+  static constexpr int V_OFF = K_OFF + KV_STAGES * 16384;
+  static constexpr int BAR_OFF = V_OFF + KV_STAGES * 16384;
+  static constexpr int NUM_BARS = 4 + 3 * KV_STAGES + 8;
+  static constexpr int SMEM_BYTES = BAR_OFF + NUM_BARS * 8 + 16;
+  static constexpr int THREADS = 384;
+  static constexpr int TMEM_COLS = 512;
+};
+
+template <int POLY = 0, int MODE = 0>
+__global__ void __launch_bounds__(AttnPersistCfg::THREADS, 1)
+attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+  using Cfg = AttnPersistCfg;
+  constexpr bool PT = true;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* q_full = bars;                       // [2]  producer -> MMA / softmax : Q buffer landed
+  uint64_t* q_empty = bars + 2;                  // [2]  MMA commit + the 2 output-store threads -> producer : Q buffer reusable
+  uint64_t* k_full = bars + 4;
+  uint64_t* v_full = k_full + Cfg::KV_STAGES;
+  uint64_t* kv_empty = v_full + Cfg::KV_STAGES;
+  uint64_t* s_full = kv_empty + Cfg::KV_STAGES;
+  uint64_t* s_free = s_full + 2;
+  uint64_t* p_ready = s_free + 2;
+  uint64_t* o_done = p_ready + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G_CTAS = gridDim.x, cta = blockIdx.x;
+  const int nqb = (p.Nq_total - p.q_start + 2 * Cfg::TQ - 1) / (2 * Cfg::TQ);
+  const int rows_last = p.Nq_total - p.q_start - (nqb - 1) * 2 * Cfg::TQ;
+  const int has_tail = rows_last <= p.tail_rows_max ? 1 : 0;
+  const int nqb_reg = nqb - has_tail;
+  const int n_reg = p.B * p.H * nqb_reg;          // host guarantees n_reg >= gridDim.x
+  const int n_tail = p.B * p.H * has_tail;
+  const int koff = p.peel_key0 ? 1 : 0;
+  const int nk_eff = p.Nk - koff;
+  const int T = (nk_eff + Cfg::TKV - 1) / Cfg::TKV;
+  const int last_valid = nk_eff - (T - 1) * Cfg::TKV;
+  const int last_cols16 = (last_valid + 15) & ~15;
+  // regular items r = first_r, first_r + G_CTAS, ...: the CTAs are walked backwards so that the ones that serve an extra
+  // tail row (low ids) are not the ones that get the remainder of the regular items
+  const int first_r = G_CTAS - 1 - cta;
+  const int n_items = (n_reg - first_r + G_CTAS - 1) / G_CTAS;
+  const int G = n_items * T;                      // KV tiles this CTA processes per query tile
+
+  // ---- tail rows first (whole CTA, plain loads, shared memory not yet in use) ----
+  for (int t = cta; t < n_tail; t += G_CTAS) {
+    const int h = t % p.H, b = t / p.H;
+    attn_tail_rows(p.q + (long long)b * p.q_bs + p.q_col0 + h * 64, p.k + (long long)b * p.k_bs + p.k_col0 + h * 64,
+                   p.v + (long long)b * p.v_bs + p.v_col0 + h * 64, p.out + (long long)b * p.out_batch_stride + h * 64, p.ldq, p.ldk,
+                   p.ldv, p.ldo, p.Nk, p.scale_log2, p.q_start + nqb_reg * 2 * Cfg::TQ, rows_last, smem);
+  }
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("dclip attn: dynamic smem base not 1024B aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 3);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&o_done[i], 1);
+    }
+    for (int s = 0; s < Cfg::KV_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 10) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+    setmaxnreg_dec<80>();
+    if (warp == 9) {
+      // ------------------------------- TMA producer -------------------------------
+      if (lane == 0) {
+        int g = 0;
+        for (int n = 0; n < n_items; ++n) {
+          const int r = first_r + n * G_CTAS;
+          const int qb = r % nqb_reg, h = (r / nqb_reg) % p.H, b = r / (nqb_reg * p.H);
+          const int q_row0 = p.q_start + qb * 2 * Cfg::TQ;
+          const int qbuf = n & 1;
+          if (n >= 2) mbar_wait(&q_empty[qbuf], ((n >> 1) - 1) & 1);
+          mbar_arrive_expect_tx(&q_full[qbuf], 2 * 16384);
+          tma_load_3d(smem + Cfg::Q_OFF + qbuf * 32768, &tmQ, &q_full[qbuf], p.q_col0 + h * Cfg::HD, q_row0, b);
+          tma_load_3d(smem + Cfg::Q_OFF + qbuf * 32768 + 16384, &tmQ, &q_full[qbuf], p.q_col0 + h * Cfg::HD, q_row0 + Cfg::TQ, b);
+          for (int j = 0; j < T; ++j, ++g) {
+            const int s = g % Cfg::KV_STAGES;
+            const uint32_t ph = (g / Cfg::KV_STAGES) & 1;
+            mbar_wait(&kv_empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&k_full[s], 16384);
+            tma_load_3d(smem + Cfg::K_OFF + s * 16384, &tmK, &k_full[s], p.k_col0 + h * Cfg::HD, koff + j * Cfg::TKV, b);
+            mbar_arrive_expect_tx(&v_full[s], 16384);
+            tma_load_3d(smem + Cfg::V_OFF + s * 16384, &tmV, &v_full[s], p.v_col0 + h * Cfg::HD, koff + j * Cfg::TKV, b);
+          }
+        }
+      }
+    } else if (warp == 8) {
+      // ------------------------------- MMA issuer ----------------------------------
+      const uint64_t dQ = make_smem_desc_sw128(smem_u32(smem + Cfg::Q_OFF), 16, 1024);
+      const uint64_t dK = make_smem_desc_sw128(smem_u32(smem + Cfg::K_OFF), 16, 1024);
+      const uint64_t dV = make_smem_desc_sw128(smem_u32(smem + Cfg::V_OFF), 16, 1024);
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t idesc_qk_last = make_idesc_bf16(128, last_cols16);
+      // QK^T of query tile i against global KV tile g (item n = g / T, tile j = g % T of that item)
+      auto issue_qk = [&](int i, int g, int n, int j) {
+        const int stage = g % Cfg::KV_STAGES;
+        const uint64_t a = dQ + uint64_t(n & 1) * 2048 + uint64_t(i) * 1024, bb = dK + uint64_t(stage) * 1024;
+        const uint32_t idesc = (j == T - 1) ? idesc_qk_last : idesc_qk;
+        const uint32_t d = tmem_base + i * 128;
+        const bool release_q = (i == 1 && j == T - 1);  // last QK^T that reads this item's Q buffer
+        if (elect_one_sync()) {
+          umma_ss_f16(d, a, bb, idesc, 0u);
+          umma_ss_f16(d, a + 2, bb + 2, idesc, 1u);
+          umma_ss_f16(d, a + 4, bb + 4, idesc, 1u);
+          umma_ss_f16(d, a + 6, bb + 6, idesc, 1u);
+          umma_commit(&s_full[i]);
+          if (release_q) umma_commit(&q_empty[n & 1]);
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int i, int stage, bool is_last, uint32_t acc, bool release_kv) {
+        const uint64_t bb = dV + uint64_t(stage) * 1024;
+        const uint32_t d = tmem_base + 256 + i * 64;
+        const uint32_t ta = tmem_base + 384 + i * 64;
+        if (elect_one_sync()) {
+          if (!is_last || last_cols16 == 128) {
+            umma_ts_f16(d, ta, bb, idesc_pv, acc);
+#pragma unroll
+            for (int ks = 1; ks < 8; ++ks) umma_ts_f16(d, ta + ks * 8, bb + ks * 128, idesc_pv, 1u);
+          } else {
+            for (int ks = 0; ks < last_cols16 / 16; ++ks)
+              umma_ts_f16(d, ta + ks * 8, bb + ks * 128, idesc_pv, (acc | ks) ? 1u : 0u);
+          }
+          umma_commit(&o_done[i]);
+          if (release_kv) umma_commit(&kv_empty[stage]);
+        }
+        __syncwarp();
+      };
+      // prologue: tiles g = 0 and g = 1
+      mbar_wait(&q_full[0], 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0, 0, 0);
+      issue_qk(1, 0, 0, 0);
+      if (G > 1) {
+        const int n1 = (T == 1) ? 1 : 0, j1 = (T == 1) ? 0 : 1;
+        if (n1) mbar_wait(&q_full[1], 0);
+        mbar_wait(&k_full[1 % Cfg::KV_STAGES], (1 / Cfg::KV_STAGES) & 1);
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(&s_free[i], 0);
+          tc_fence_after();
+          issue_qk(i, 1, n1, j1);
+        }
+      }
+      int j = 0;                                  // tile index of g inside its item
+      int n2 = (T <= 2) ? 2 / T : 0, j2 = 2 % T;  // item / tile index of g + 2
+      for (int g = 0; g < G; ++g) {
+        const int s = g % Cfg::KV_STAGES;
+        mbar_wait(&v_full[s], (g / Cfg::KV_STAGES) & 1);
+        // Steady state: PV(0), QK^T(0, g+2), PV(1), QK^T(1, g+2) -- the blocking s_free wait behind PV(0) keeps the two
+        // warpgroups half a step apart.  Last tile of an item: both PVs first; there the s_free arrivals come only after
+        // each warpgroup's output pass, and a blocked MMA warp would serialise the two output passes.
+        const bool boundary = (j == T - 1);
+        const int g2 = g + 2;
+        const bool more = g2 < G;
+        if (more) {
+          mbar_wait(&k_full[g2 % Cfg::KV_STAGES], (g2 / Cfg::KV_STAGES) & 1);
+          if (j2 == 0) mbar_wait(&q_full[n2 & 1], (n2 >> 1) & 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(&p_ready[i], g & 1);
+          tc_fence_after();
+          DCLIP_TL(if (p.dbg && blockIdx.x == p.dbg_cta && g >= T - 2 && g < T - 2 + 31) p.dbg[512 + (i * 32 + g - (T - 2)) * 2] = clock64();)
+          issue_pv(i, s, j == T - 1, j > 0 ? 1u : 0u, i == 1);
+          if (more && !boundary) {
+            mbar_wait(&s_free[i], (g + 1) & 1);
+            tc_fence_after();
+            DCLIP_TL(if (p.dbg && blockIdx.x == p.dbg_cta && g2 >= T - 2 && g2 < T - 2 + 31) p.dbg[512 + (i * 32 + g2 - (T - 2)) * 2 + 1] = clock64();)
+            issue_qk(i, g2, n2, j2);
+          }
+        }
+        if (more && boundary) {
+          for (int i = 0; i < 2; ++i) {
+            mbar_wait(&s_free[i], (g + 1) & 1);
+            tc_fence_after();
+            DCLIP_TL(if (p.dbg && blockIdx.x == p.dbg_cta && g2 >= T - 2 && g2 < T - 2 + 31) p.dbg[512 + (i * 32 + g2 - (T - 2)) * 2 + 1] = clock64();)
+            issue_qk(i, g2, n2, j2);
+          }
+        }
+        if (++j == T) j = 0;
+        if (++j2 == T) { j2 = 0; ++n2; }
+      }
+    }
+  } else {
+    // ------------------------------- softmax warpgroups --------------------------
+    setmaxnreg_inc<208>();
+    constexpr bool SPEC = (MODE & 1) != 0, DEFER = (MODE & 2) != 0;
+    const int i = warp >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = uint32_t(q * 32) << 16;
+    const uint32_t tS = tmem_base + i * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + i * 64 + lane_off;
+    const uint32_t tP = tmem_base + 384 + i * 64 + lane_off;
+    const float sc = p.scale_log2;
+    if (i == 1 && p.token_mode) named_bar_arrive(1, 256);  // WG0 owns the MUFU token first
+    int g = 0;
+    for (int n = 0; n < n_items; ++n) {
+      const int ritem = first_r + n * G_CTAS;
+      const int qb = ritem % nqb_reg, h = (ritem / nqb_reg) % p.H, b = ritem / (nqb_reg * p.H);
+      const int q_row0 = p.q_start + qb * 2 * Cfg::TQ;
+      if (koff && lane == 0) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.k + (long long)b * p.k_bs + p.k_col0 + h * Cfg::HD));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.v + (long long)b * p.v_bs + p.v_col0 + h * Cfg::HD));
+      }
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = 0; j < T; ++j, ++g) {
+        long long* dbg = nullptr;
+        DCLIP_TL(if (p.dbg && blockIdx.x == p.dbg_cta && (warp & 3) == 0 && lane == 0 && g >= T - 2 && g < T - 2 + 31) dbg = p.dbg + (i * 32 + g - (T - 2)) * 8;)
+        DCLIP_TL(if (dbg) dbg[6] = clock64();)
+        mbar_wait(&s_full[i], g & 1);
+        tc_fence_after();
+        DCLIP_TL(if (dbg) dbg[0] = clock64();)
+        const int valid = (j + 1 == T) ? last_valid : 128;
+        const bool last_tile = g + 1 == G;
+        const uint32_t odp = (g - 1) & 1;
+        if (SPEC && j > 0) {
+          if (valid > 32)
+            attn_softmax_tile_spec<128, PT, POLY, DEFER>(tS, tO, tP, nullptr, r, lane, valid, sc, m_used, l, &s_free[i], &o_done[i], odp, i, last_tile, p.token_mode, nullptr);
+          else
+            attn_softmax_tile_spec<32, PT, POLY, DEFER>(tS, tO, tP, nullptr, r, lane, valid, sc, m_used, l, &s_free[i], &o_done[i], odp, i, last_tile, p.token_mode, nullptr);
+        } else if (valid > 32)
+          attn_softmax_tile<128, PT, POLY, false>(tS, tO, tP, nullptr, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], odp, i, last_tile, p.token_mode, dbg);
+        else
+          attn_softmax_tile<32, PT, POLY, false>(tS, tO, tP, nullptr, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], odp, i, last_tile, p.token_mode, dbg);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[i]);
+        DCLIP_TL(if (dbg) dbg[5] = clock64();)
+        if (j == 0 && n > 0 && q == 0 && lane == 0) {
+          // the previous item's output tile sits in its Q buffer until the TMA store has read it (long done by now);
+          // only then may the producer refill that buffer (it needs it a whole item from now)
+          tma_store_wait_read();
+          mbar_arrive(&q_empty[(n - 1) & 1]);
+        }
+      }
+      // ---- output pass of this item (the MMA warp is already on the next item's first tiles) ----
+      long long* edbg = nullptr;
+      DCLIP_TL(if (p.dbg && blockIdx.x == p.dbg_cta && (warp & 3) == 0 && lane == 0 && n == 1) edbg = p.dbg + (i * 32 + 31) * 8;)
+      DCLIP_TL(if (edbg) edbg[6] = clock64();)
+      float z0 = 0.f;
+      uint4 v0r[8];
+      if (koff) {
+        const uint4* k0 = reinterpret_cast<const uint4*>(p.k + (long long)b * p.k_bs + p.k_col0 + h * Cfg::HD);
+        const uint4* v0 = reinterpret_cast<const uint4*>(p.v + (long long)b * p.v_bs + p.v_col0 + h * Cfg::HD);
+        const uint8_t* qrow = smem + Cfg::Q_OFF + (n & 1) * 32768 + i * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4));
+          const uint4 kv = __ldg(k0 + c);
+          v0r[c] = __ldg(v0 + c);
+          const uint32_t qq[4] = {qv.x, qv.y, qv.z, qv.w}, kk[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            s0 = fmaf(__uint_as_float(qq[e] << 16), __uint_as_float(kk[e] << 16), s0);
+            s1 = fmaf(__uint_as_float(qq[e] & 0xffff0000u), __uint_as_float(kk[e] & 0xffff0000u), s1);
+          }
+        }
+        z0 = (s0 + s1) * sc;
+      }
+      DCLIP_TL(if (edbg) edbg[0] = clock64();)
+      mbar_wait(&o_done[i], (g - 1) & 1);
+      tc_fence_after();
+      DCLIP_TL(if (edbg) edbg[1] = clock64();)
+      float alpha = 1.0f, p0 = 0.f;
+      if (koff) {
+        const float e0 = z0 - m_used * sc;
+        alpha = e0 > 0.f ? ex2_approx(-e0) : 1.0f;
+        p0 = e0 > 0.f ? 1.0f : ex2_approx(e0);
+        l = l * alpha + p0;
+      }
+      const float inv = 1.0f / l;
+      alpha *= inv;
+      p0 *= inv;
+      uint8_t* q_tile = smem + Cfg::Q_OFF + (n & 1) * 32768 + i * 16384;
+      attn_store_tile(tO, q_tile, r, alpha, p0, koff != 0, v0r);
+      DCLIP_TL(if (edbg) edbg[2] = clock64();)
+      named_bar_sync(3 + i, 128);
+      DCLIP_TL(if (edbg) edbg[3] = clock64();)
+      if (q == 0 && lane == 0) {
+        tma_store_3d(&tmO, q_tile, h * Cfg::HD, q_row0 + i * Cfg::TQ, b);
+        tma_store_commit();
+      }
+      DCLIP_TL(if (edbg) edbg[5] = clock64();)
+      tc_fence_before();  // the O reads are ordered before this warp's next p_ready arrive (next item's first PV overwrites O)
+    }
+    if (q == 0 && lane == 0) tma_store_wait_read();  // last item's tile: shared memory must outlive the store's reads
   }
 
   tc_fence_before();

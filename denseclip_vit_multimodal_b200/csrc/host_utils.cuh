@@ -347,8 +347,9 @@ inline CUtensorMap make_tmap_tokens_bf16(const void* base, uint64_t B, uint64_t 
   return make_tmap_bf16(base, 3, dims, str, box);
 }
 
+using Cfg128 = AttnCfg;
 struct AttnPlan {
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmO;
   AttnParams p;
   int grid = 0;
 };
@@ -371,6 +372,8 @@ inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
   plan.p.q = op.q; plan.p.k = op.k; plan.p.v = op.v;
   plan.p.ldq = op.ldq; plan.p.ldk = op.ldk; plan.p.ldv = op.ldv;
   plan.p.q_bs = op.q_bs; plan.p.k_bs = op.k_bs; plan.p.v_bs = op.v_bs;
+  static const int peel_env = [] { const char* e = getenv("DCLIP_ATTN_PEEL"); return e ? atoi(e) : 1; }();
+  plan.p.peel_key0 = (peel_env && p.Nk > Cfg128::TKV && (p.Nk - 1) % Cfg128::TKV == 0) ? 1 : 0;
   // the CUDA-core tail path keeps one fp32 score per key in shared memory
   plan.p.tail_rows_max = (size_t(p.Nk) * 4 + 16384 <= size_t(AttnCfg::SMEM_BYTES)) ? tail_env : 0;
   DCLIP_REQUIRE(op.ldq % 8 == 0 && op.ldk % 8 == 0 && op.ldv % 8 == 0 && p.q_col0 % 8 == 0 && p.k_col0 % 8 == 0 && p.v_col0 % 8 == 0 &&
@@ -378,6 +381,7 @@ inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
   plan.tmQ = make_tmap_tokens_bf16(op.q, p.B, op.Nq_total, op.ldq, op.q_bs);
   plan.tmK = make_tmap_tokens_bf16(op.k, p.B, p.Nk, op.ldk, op.k_bs);
   plan.tmV = make_tmap_tokens_bf16(op.v, p.B, p.Nk, op.ldv, op.v_bs);
+  plan.tmO = make_tmap_tokens_bf16(p.out, p.B, op.Nq_total, p.ldo, p.out_batch_stride);
   const int nqb = (p.Nq_total - p.q_start + 255) / 256;
   plan.grid = nqb * p.H * p.B;
   return plan;
@@ -391,7 +395,19 @@ inline void run_attn_variant(const AttnPlan& plan, cudaStream_t stream) {
     DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<PT, POLY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  attn_fwd_tcgen05_kernel<PT, POLY, MODE><<<plan.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.p);
+  attn_fwd_tcgen05_kernel<PT, POLY, MODE><<<plan.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.tmO, plan.p);
+  DCLIP_CHECK_CUDA(cudaGetLastError());
+}
+
+template <int POLY>
+inline void run_attn_persistent(const AttnPlan& plan, int grid, cudaStream_t stream) {
+  using Cfg = AttnPersistCfg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_persistent_kernel<POLY, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  attn_fwd_persistent_kernel<POLY, 0><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.tmO, plan.p);
   DCLIP_CHECK_CUDA(cudaGetLastError());
 }
 
@@ -403,6 +419,9 @@ inline void run_attn_variant(const AttnPlan& plan, cudaStream_t stream) {
 #ifndef DCLIP_ATTN_SPEC_DEFAULT
 #define DCLIP_ATTN_SPEC_DEFAULT 0  // speculative-max softmax tiles (measured slower with the MUFU token: 0.366 vs 0.349 ms)
 #endif
+#ifndef DCLIP_ATTN_PERSIST_DEFAULT
+#define DCLIP_ATTN_PERSIST_DEFAULT 1  // persistent one-CTA-per-SM kernel (attn_fwd_persistent_kernel)
+#endif
 #ifndef DCLIP_ATTN_DEFER_DEFAULT
 #define DCLIP_ATTN_DEFER_DEFAULT 0  // deferred P stores (measured slower: 0.373 vs 0.349 ms, profiles/r01_attention_notes.md)
 #endif
@@ -411,6 +430,19 @@ inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
   static const int poly = [] { const char* e = getenv("DCLIP_ATTN_POLY"); return e ? atoi(e) : DCLIP_ATTN_POLY_DEFAULT; }();
   static const int spec = [] { const char* e = getenv("DCLIP_ATTN_SPEC"); return e ? atoi(e) : DCLIP_ATTN_SPEC_DEFAULT; }();
   static const int defer = [] { const char* e = getenv("DCLIP_ATTN_DEFER"); return e ? atoi(e) : DCLIP_ATTN_DEFER_DEFAULT; }();
+  static const int persist = [] { const char* e = getenv("DCLIP_ATTN_PERSIST"); return e ? atoi(e) : DCLIP_ATTN_PERSIST_DEFAULT; }();
+  if (persist && !p_smem && !spec && !defer) {
+    // persistent kernel: one CTA per SM over a static item list (needs at least one regular 256-query block per CTA)
+    const AttnParams& q = plan.p;
+    const int nqb = (q.Nq_total - q.q_start + 255) / 256;
+    const int rows_last = q.Nq_total - q.q_start - (nqb - 1) * 256;
+    const int n_reg = q.B * q.H * (nqb - (rows_last <= q.tail_rows_max ? 1 : 0));
+    if (n_reg > 0) {
+      const int grid = n_reg < sm_count() ? n_reg : sm_count();
+      if (poly) return run_attn_persistent<1>(plan, grid, stream);
+      return run_attn_persistent<0>(plan, grid, stream);
+    }
+  }
   if (p_smem) return run_attn_variant<false, 0, 0>(plan, stream);
   switch ((poly ? 4 : 0) | (defer ? 2 : 0) | (spec ? 1 : 0)) {
     case 0: return run_attn_variant<true, 0, 0>(plan, stream);

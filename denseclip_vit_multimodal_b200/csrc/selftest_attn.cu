@@ -134,11 +134,11 @@ int main(int argc, char** argv) {
     fill_bf16<<<(size_t(B) * N * ld + 255) / 256, 256>>>(qkv, size_t(B) * N * ld, 11u, 2.0f);
     AttnOperands op{qkv, qkv, qkv, ld, ld, ld, (long long)N * ld, (long long)N * ld, (long long)N * ld, N};
     AttnParams p{};
-    p.B = B; p.H = H; p.Nq_total = N; p.q_start = 1; p.Nk = N; p.q_col0 = 0; p.k_col0 = D; p.v_col0 = 2 * D;
+    p.B = B; p.H = H; p.Nq_total = N; p.q_start = getenv("DCLIP_TL_QSTART") ? atoi(getenv("DCLIP_TL_QSTART")) : 1; p.Nk = N; p.q_col0 = 0; p.k_col0 = D; p.v_col0 = 2 * D;
     p.scale_log2 = 0.125f * 1.4426950408889634f; p.out = out; p.out_batch_stride = (long long)N * D; p.ldo = D;
     for (int rep = 0; rep < 2; ++rep) {
       cudaMemset(dbg, 0, 1024 * 8);
-      p.dbg = dbg; p.dbg_cta = rep == 0 ? 0 : 700;
+      p.dbg = dbg; p.dbg_cta = rep == 0 ? 0 : (getenv("DCLIP_TL_CTA") ? atoi(getenv("DCLIP_TL_CTA")) : 700);
       AttnPlan plan = make_attn_plan(op, p);
       run_attn(plan, 0);
       cudaDeviceSynchronize();
@@ -146,7 +146,8 @@ int main(int argc, char** argv) {
       cudaMemcpy(h.data(), dbg, 1024 * 8, cudaMemcpyDeviceToHost);
       long long t0 = h[6];
       printf("timeline CTA %d (cycles rel. to first wait)  cols: wait_start s_full_got ld_done max_done exps_done o_done_got arrived | mma: pv_issue qk_issue\n", p.dbg_cta);
-      for (int j = 0; j < 17; ++j)
+      const int nrows = getenv("DCLIP_TL_ROWS") ? atoi(getenv("DCLIP_TL_ROWS")) : 17;
+      for (int j = 0; j < nrows; ++j)
         for (int i = 0; i < 2; ++i) {
           const long long* d = &h[(i * 32 + j) * 8];
           printf("wg%d j=%2d  %7lld %7lld %7lld %7lld %7lld %7lld %7lld | %7lld %7lld\n", i, j, d[6] - t0, d[0] - t0, d[1] - t0, d[2] - t0,

@@ -8,8 +8,14 @@ for r in rows:
     if r[0]=='ID': hdr=r; continue
     if hdr and r[0].isdigit(): data.append(r)
 iname=hdr.index('Kernel Name'); ival=hdr.index('Metric Value'); iunit=hdr.index('Metric Unit')
-n=int(sys.argv[2]) if len(sys.argv)>2 else len(data)//3
-last=data[-n:]
+# one forward = the launches from one patch-im2col kernel (first kernel of the encoder) to the next one
+marks=[i for i,r in enumerate(data) if 'im2col_patch' in r[iname]]
+if len(sys.argv)>2:
+    n=int(sys.argv[2]); last=data[-n:]
+elif len(marks)>=2:
+    last=data[marks[-2]:marks[-1]]; n=len(last)
+else:
+    n=len(data)//3; last=data[-n:]
 agg=collections.OrderedDict()
 for r in last:
     name=re.sub(r'\(.*','',r[iname]); name=name.replace('void ','').replace('dclip::','')
