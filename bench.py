@@ -31,7 +31,7 @@ ENCODER_FLOPS_PER_IMAGE = 505.25e9          # patch 2.416 + QKV 87.
 ATTN_FLOPS_PER_IMAGE_LAYER = 154.770e9 / 12  # QK^T + PV, 12 heads x 2049^2 x 64 x 2 x 2
 # measured on this pool's B200s by the driver (MEASURED_PEAKS.json at the time of writing); re-read from the file if present
 RECORDED_PEAKS = {"hbm_gbs": 6541.8, "bf16_tflops": 1674.0, "bf16_tflops_sustained": 1403.8}
-ATTN_DRAM_TRAFFIC_BYTES = 183.0e6           # profiles/r01_attn_ncu_final.txt (ncu --set full): dram read 151.1 MB + write 31.9 MB per launch (B=16)
+ATTN_DRAM_TRAFFIC_BYTES = 265.0e6           # profiles/r01_attn_ncu_persistent.txt (ncu --set full): dram read 233.5 MB + write 31.5 MB per launch (B=16)
 
 
 def peaks():
@@ -334,7 +334,7 @@ def main():
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "PipelinedPredictor(DenseCLIP.predict): pinned host images in, uint8 class map + fp32 depth back on the host, every step; copies overlap compute (wall-clock timed)"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "attn_fwd_tcgen05_kernel (flash attention, 12 launches/step)", "bound": "tensor",
+            "roofline": {"kernel": "attn_fwd_persistent_kernel (tcgen05 flash attention, one CTA per SM, 12 launches/step)", "bound": "tensor",
                          "achieved": attn_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": attn_tflops / pk["bf16_tflops"],
                          "traffic": ATTN_DRAM_TRAFFIC_BYTES * B / 16, "ms_per_launch": attn_ms, "peak_source": pk_src + " (burst: kernel timed alone)"},
             "encoder": {"ms_per_step": enc_ms, "tflops": enc_tflops, "flops_per_image": ENCODER_FLOPS_PER_IMAGE,

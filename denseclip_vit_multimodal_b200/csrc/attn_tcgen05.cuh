@@ -511,7 +511,7 @@ __device__ __forceinline__ void attn_store_tile(uint32_t tO, uint8_t* q_tile, in
                                                 const uint4 (&v0r)[8]) {
   uint8_t* srow = q_tile + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
+  for (int c = 0; c < 2; ++c) {  // (both 32-column loads in flight at once measured slower: register pressure)
     uint32_t o[32];
     tmem_ld_32x32b_x32(tO + c * 32, o);
     tmem_wait_ld();
@@ -580,6 +580,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
     mbar_init(q_full, 1);
     for (int s = 0; s < Cfg::KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
@@ -726,18 +727,24 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const float sc = p.scale_log2;
     float m_used = -INFINITY, l = 0.f;
     if (i == 1 && p.token_mode) named_bar_arrive(1, 256);  // WG0 owns the MUFU token first
-    // peeled key 0 (koff): its score and its P*V term are computed on CUDA cores in the output pass; here only park the
-    // two 128 B lines (k_0, v_0 of this head) in L1 -- the K/V stream goes through TMA and never touches L1
-    if (koff && lane == 0) {
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.k + (long long)b * p.k_bs + p.k_col0 + h * Cfg::HD));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.v + (long long)b * p.v_bs + p.v_col0 + h * Cfg::HD));
-    }
-
     for (int j = 0; j < T; ++j) {
       DCLIP_TL(if (p.dbg && blockIdx.x == p.dbg_cta && (warp & 3) == 0 && lane == 0) p.dbg[(i * 32 + j) * 8 + 6] = clock64();)
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
       const int valid = (j + 1 == T) ? last_valid : 128;
+      // peeled key 0 (koff): its score and its P*V term are computed on CUDA cores in the output pass; one tile ahead, park
+      // the two 128 B lines (k_0, v_0 of this head) in L1 -- the K/V stream goes through TMA and never touches L1
+      if (koff && lane == 0 && (j + 1 == T || (p.peel_key0 == 2 && (j == 0 || j + 2 == T)))) {
+        const __nv_bfloat16* k0p = p.k + (long long)b * p.k_bs + p.k_col0 + h * Cfg::HD;
+        const __nv_bfloat16* v0p = p.v + (long long)b * p.v_bs + p.v_col0 + h * Cfg::HD;
+        if (j == 0) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(k0p));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(v0p));
+        } else {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(k0p));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(v0p));
+        }
+      }
       long long* dbg = nullptr;
       DCLIP_TL(dbg = (p.dbg && blockIdx.x == p.dbg_cta && (warp & 3) == 0 && lane == 0) ? p.dbg + (i * 32 + j) * 8 : nullptr;)
       DCLIP_TL(if (dbg) dbg[0] = clock64();)
@@ -890,6 +897,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 3);
@@ -1004,29 +1012,21 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       for (int g = 0; g < G; ++g) {
         const int s = g % Cfg::KV_STAGES;
         mbar_wait(&v_full[s], (g / Cfg::KV_STAGES) & 1);
-        // Steady state: PV(0), QK^T(0, g+2), PV(1), QK^T(1, g+2) -- the blocking s_free wait behind PV(0) keeps the two
-        // warpgroups half a step apart.  Last tile of an item: both PVs first; there the s_free arrivals come only after
-        // each warpgroup's output pass, and a blocked MMA warp would serialise the two output passes.
-        const bool boundary = (j == T - 1);
+        // Both PVs first, then both QK^T of tile g + 2 (not needed for another ~2 steps): a warpgroup that is late with
+        // s_free -- its output pass at an item boundary -- must not hold up the other warpgroup's PV.  (Keeping the
+        // non-persistent order PV0 QK0 PV1 QK1 in steady state and reordering only the boundary tile measured slower:
+        // 0.318 vs 0.312 ms.)
         const int g2 = g + 2;
         const bool more = g2 < G;
-        if (more) {
-          mbar_wait(&k_full[g2 % Cfg::KV_STAGES], (g2 / Cfg::KV_STAGES) & 1);
-          if (j2 == 0) mbar_wait(&q_full[n2 & 1], (n2 >> 1) & 1);
-        }
         for (int i = 0; i < 2; ++i) {
           mbar_wait(&p_ready[i], g & 1);
           tc_fence_after();
           DCLIP_TL(if (p.dbg && blockIdx.x == p.dbg_cta && g >= T - 2 && g < T - 2 + 31) p.dbg[512 + (i * 32 + g - (T - 2)) * 2] = clock64();)
           issue_pv(i, s, j == T - 1, j > 0 ? 1u : 0u, i == 1);
-          if (more && !boundary) {
-            mbar_wait(&s_free[i], (g + 1) & 1);
-            tc_fence_after();
-            DCLIP_TL(if (p.dbg && blockIdx.x == p.dbg_cta && g2 >= T - 2 && g2 < T - 2 + 31) p.dbg[512 + (i * 32 + g2 - (T - 2)) * 2 + 1] = clock64();)
-            issue_qk(i, g2, n2, j2);
-          }
         }
-        if (more && boundary) {
+        if (more) {
+          mbar_wait(&k_full[g2 % Cfg::KV_STAGES], (g2 / Cfg::KV_STAGES) & 1);
+          if (j2 == 0) mbar_wait(&q_full[n2 & 1], (n2 >> 1) & 1);
           for (int i = 0; i < 2; ++i) {
             mbar_wait(&s_free[i], (g + 1) & 1);
             tc_fence_after();
@@ -1056,10 +1056,6 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       const int ritem = first_r + n * G_CTAS;
       const int qb = ritem % nqb_reg, h = (ritem / nqb_reg) % p.H, b = ritem / (nqb_reg * p.H);
       const int q_row0 = p.q_start + qb * 2 * Cfg::TQ;
-      if (koff && lane == 0) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.k + (long long)b * p.k_bs + p.k_col0 + h * Cfg::HD));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.v + (long long)b * p.v_bs + p.v_col0 + h * Cfg::HD));
-      }
       float m_used = -INFINITY, l = 0.f;
       for (int j = 0; j < T; ++j, ++g) {
         long long* dbg = nullptr;
@@ -1070,6 +1066,19 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         DCLIP_TL(if (dbg) dbg[0] = clock64();)
         const int valid = (j + 1 == T) ? last_valid : 128;
         const bool last_tile = g + 1 == G;
+        if (koff && lane == 0 && (j + 1 == T || (p.peel_key0 == 2 && (j == 0 || j + 2 == T)))) {
+          // k_0 / v_0 of this head are touched by nobody else: pull them into L2 at the start of the item (HBM miss,
+          // ~1.5 us) and into L1 over the last two tiles, so the output pass finds them there
+          const __nv_bfloat16* k0p = p.k + (long long)b * p.k_bs + p.k_col0 + h * Cfg::HD;
+          const __nv_bfloat16* v0p = p.v + (long long)b * p.v_bs + p.v_col0 + h * Cfg::HD;
+          if (j == 0) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(k0p));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(v0p));
+          } else {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(k0p));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(v0p));
+          }
+        }
         const uint32_t odp = (g - 1) & 1;
         if (SPEC && j > 0) {
           if (valid > 32)

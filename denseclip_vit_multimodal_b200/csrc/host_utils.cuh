@@ -373,7 +373,7 @@ inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
   plan.p.ldq = op.ldq; plan.p.ldk = op.ldk; plan.p.ldv = op.ldv;
   plan.p.q_bs = op.q_bs; plan.p.k_bs = op.k_bs; plan.p.v_bs = op.v_bs;
   static const int peel_env = [] { const char* e = getenv("DCLIP_ATTN_PEEL"); return e ? atoi(e) : 1; }();
-  plan.p.peel_key0 = (peel_env && p.Nk > Cfg128::TKV && (p.Nk - 1) % Cfg128::TKV == 0) ? 1 : 0;
+  plan.p.peel_key0 = (peel_env && p.Nk > Cfg128::TKV && (p.Nk - 1) % Cfg128::TKV == 0) ? peel_env : 0;  // 2: also L2 / early L1 prefetch of k_0, v_0
   // the CUDA-core tail path keeps one fp32 score per key in shared memory
   plan.p.tail_rows_max = (size_t(p.Nk) * 4 + 16384 <= size_t(AttnCfg::SMEM_BYTES)) ? tail_env : 0;
   DCLIP_REQUIRE(op.ldq % 8 == 0 && op.ldk % 8 == 0 && op.ldv % 8 == 0 && p.q_col0 % 8 == 0 && p.k_col0 % 8 == 0 && p.v_col0 % 8 == 0 &&
