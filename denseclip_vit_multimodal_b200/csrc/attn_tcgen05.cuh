@@ -38,6 +38,8 @@ struct AttnParams {
   int ldq, ldk, ldv;
   long long q_bs, k_bs, v_bs;
   int tail_rows_max;           // query blocks with <= this many valid rows take the CUDA-core path (0 = never)
+  int tail_overlap;            // persistent kernel: 1 = the tail rows are served by the two idle control warps WHILE the tensor-core
+                               //    pipeline runs (attn_tail_rows_bg), 0 = by the whole CTA before the pipeline starts
   int peel_key0;               // 1: key 0 is handled on CUDA cores (score in the prologue, P*V in the output pass) and the KV tiles
                                //    cover keys 1..Nk-1 -- for Nk = 128 t + 1 (2049 tokens) this saves the whole ragged last tile
   long long* dbg;              // optional timeline buffer (selftest only): clock64 stamps of CTA `dbg_cta`
@@ -821,6 +823,99 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
+
+// Tail rows in the background of the persistent pipeline: warps 10 and 11 (64 threads, 80 registers) = 8 key-row groups of
+// 8 threads.  Group g walks keys g, g + 8, ... four at a time with an online softmax (running max / sum / 8 output dims per
+// thread), so no per-key score buffer is needed; the 8 partial results are merged through 2.1 KB of shared memory.
+// ~60 us per row, hidden behind the ~300 us the tensor-core pipeline of the same CTA runs.
+__device__ __forceinline__ void attn_tail_rows_bg(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                                                  __nv_bfloat16* out, int ldq, int ldk, int ldv, int ldo, int Nk, float scale_log2,
+                                                  int row0, int nrows, float* s_merge, int tid64) {
+  const int g = tid64 >> 3, dq = tid64 & 7;
+  for (int rr = 0; rr < nrows; ++rr) {
+    const int row = row0 + rr;
+    float qf[8];
+    {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(q + (long long)row * ldq) + dq);
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        qf[2 * e] = __uint_as_float(ww[e] << 16) * scale_log2;
+        qf[2 * e + 1] = __uint_as_float(ww[e] & 0xffff0000u) * scale_log2;
+      }
+    }
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    const int trips = (Nk + 31) / 32;  // 8 groups x 4 keys per trip, warp-uniform
+    for (int t = 0; t < trips; ++t) {
+      uint4 kw[4], vw[4];
+      float sj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = t * 32 + u * 8 + g;
+        kw[u] = make_uint4(0u, 0u, 0u, 0u);
+        vw[u] = kw[u];
+        if (j < Nk) {
+          kw[u] = __ldg(reinterpret_cast<const uint4*>(k + (long long)j * ldk) + dq);
+          vw[u] = __ldg(reinterpret_cast<const uint4*>(v + (long long)j * ldv) + dq);
+        }
+      }
+      float mt = m;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = t * 32 + u * 8 + g;
+        const uint32_t ww[4] = {kw[u].x, kw[u].y, kw[u].z, kw[u].w};
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s0 = fmaf(qf[2 * e], __uint_as_float(ww[e] << 16), s0);
+          s1 = fmaf(qf[2 * e + 1], __uint_as_float(ww[e] & 0xffff0000u), s1);
+        }
+        float x = s0 + s1;
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        x += __shfl_xor_sync(0xffffffffu, x, 4);
+        sj[u] = j < Nk ? x : -INFINITY;
+        mt = fmaxf(mt, sj[u]);
+      }
+      const float corr = ex2_approx(m - mt);  // m = -inf on the first trip -> 0 (mt is finite: key g < Nk exists for Nk >= 8)
+      m = mt;
+      l *= corr;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] *= corr;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float pu = ex2_approx(sj[u] - m);
+        l += pu;
+        const uint32_t ww[4] = {vw[u].x, vw[u].y, vw[u].z, vw[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] = fmaf(pu, __uint_as_float(ww[e] << 16), acc[2 * e]);
+          acc[2 * e + 1] = fmaf(pu, __uint_as_float(ww[e] & 0xffff0000u), acc[2 * e + 1]);
+        }
+      }
+    }
+    // merge the 8 groups: s_merge[g][0..63] = acc, [64] = m, [65] = l
+    named_bar_sync(5, 64);  // previous row's merge buffer fully consumed
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_merge[g * 66 + dq * 8 + e] = acc[e];
+    if (dq == 0) { s_merge[g * 66 + 64] = m; s_merge[g * 66 + 65] = l; }
+    named_bar_sync(5, 64);
+    float mm = -INFINITY;
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg) mm = fmaxf(mm, s_merge[gg * 66 + 64]);
+    float o = 0.f, lt = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg) {
+      const float w = ex2_approx(s_merge[gg * 66 + 64] - mm);
+      o = fmaf(w, s_merge[gg * 66 + tid64], o);
+      lt = fmaf(w, s_merge[gg * 66 + 65], lt);
+    }
+    out[(long long)row * ldo + tid64] = __float2bfloat16(o / lt);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Persistent variant: one CTA per SM walks a static list of (image, head, 256-query block) items.  Per item the
 // non-persistent kernel spends ~18% of its ~30 us outside the steady-state KV loop (CTA launch, barrier / TMEM set-up,
@@ -837,10 +932,11 @@ struct AttnPersistCfg {
   static constexpr int V_OFF = K_OFF + KV_STAGES * 16384;
   static constexpr int BAR_OFF = V_OFF + KV_STAGES * 16384;
   static constexpr int NUM_BARS = 4 + 3 * KV_STAGES + 8;
-  static constexpr int SMEM_BYTES = BAR_OFF + NUM_BARS * 8 + 16;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 8 * 66 * 4;  // barriers (< 256 B) + background tail-row merge buffer
   static constexpr int THREADS = 384;
   static constexpr int TMEM_COLS = 512;
 };
+static_assert(AttnPersistCfg::NUM_BARS * 8 + 16 <= 256 && AttnPersistCfg::SMEM_BYTES <= 232448, "persistent attention smem budget");
 
 template <int POLY = 0, int MODE = 0>
 __global__ void __launch_bounds__(AttnPersistCfg::THREADS, 1)
@@ -879,9 +975,10 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   const int first_r = G_CTAS - 1 - cta;
   const int n_items = (n_reg - first_r + G_CTAS - 1) / G_CTAS;
   const int G = n_items * T;                      // KV tiles this CTA processes per query tile
+  const bool Nk_ge8 = true;                       // (host enables tail_overlap only for Nk >= 32)
 
   // ---- tail rows first (whole CTA, plain loads, shared memory not yet in use) ----
-  for (int t = cta; t < n_tail; t += G_CTAS) {
+  for (int t = cta; t < n_tail && !p.tail_overlap; t += G_CTAS) {
     const int h = t % p.H, b = t / p.H;
     attn_tail_rows(p.q + (long long)b * p.q_bs + p.q_col0 + h * 64, p.k + (long long)b * p.k_bs + p.k_col0 + h * 64,
                    p.v + (long long)b * p.v_bs + p.v_col0 + h * 64, p.out + (long long)b * p.out_batch_stride + h * 64, p.ldq, p.ldk,
@@ -946,6 +1043,18 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             mbar_arrive_expect_tx(&v_full[s], 16384);
             tma_load_3d(smem + Cfg::V_OFF + s * 16384, &tmV, &v_full[s], p.v_col0 + h * Cfg::HD, koff + j * Cfg::TKV, b);
           }
+        }
+      }
+    } else if (warp >= 10) {
+      // ------------------------------- tail rows in the background ----------------
+      if (p.tail_overlap && Nk_ge8) {
+        float* s_merge = reinterpret_cast<float*>(smem + Cfg::BAR_OFF + 256);
+        for (int t = cta; t < n_tail; t += G_CTAS) {
+          const int h = t % p.H, b = t / p.H;
+          attn_tail_rows_bg(p.q + (long long)b * p.q_bs + p.q_col0 + h * 64, p.k + (long long)b * p.k_bs + p.k_col0 + h * 64,
+                            p.v + (long long)b * p.v_bs + p.v_col0 + h * 64, p.out + (long long)b * p.out_batch_stride + h * 64,
+                            p.ldq, p.ldk, p.ldv, p.ldo, p.Nk, p.scale_log2, p.q_start + nqb_reg * 2 * Cfg::TQ, rows_last,
+                            s_merge, threadIdx.x - 320);
         }
       }
     } else if (warp == 8) {

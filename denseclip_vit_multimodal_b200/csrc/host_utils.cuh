@@ -372,6 +372,8 @@ inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
   plan.p.q = op.q; plan.p.k = op.k; plan.p.v = op.v;
   plan.p.ldq = op.ldq; plan.p.ldk = op.ldk; plan.p.ldv = op.ldv;
   plan.p.q_bs = op.q_bs; plan.p.k_bs = op.k_bs; plan.p.v_bs = op.v_bs;
+  static const int tail_ov_env = [] { const char* e = getenv("DCLIP_ATTN_TAIL_OVERLAP"); return e ? atoi(e) : 1; }();
+  plan.p.tail_overlap = (tail_ov_env && p.Nk >= 32) ? 1 : 0;  // (the online softmax of the background path assumes every key group sees a valid key in its first trip)
   static const int peel_env = [] { const char* e = getenv("DCLIP_ATTN_PEEL"); return e ? atoi(e) : 1; }();
   plan.p.peel_key0 = (peel_env && p.Nk > Cfg128::TKV && (p.Nk - 1) % Cfg128::TKV == 0) ? peel_env : 0;  // 2: also L2 / early L1 prefetch of k_0, v_0
   // the CUDA-core tail path keeps one fp32 score per key in shared memory

@@ -74,6 +74,25 @@ def test_flash_attention_vs_sdpa(ops, B, H, N):
         assert rel_err(out[:, N - tail:], ref[:, N - tail:]) < 1.5e-2
 
 
+def test_flash_attention_item_boundaries_bit_exact(ops):
+    """Persistent kernel: with 288 regular work items every CTA walks two items (shared TMEM / barriers / KV ring, Q double
+    buffer, output tile staged in the finished Q buffer).  Each image computed alone (48 items, one per CTA) must give the
+    same bits: a row's arithmetic does not depend on which CTA / item slot serves it."""
+    B, H, N = 6, 12, 1025
+    D = H * 64
+    qkv = _rand(B, N, 3 * D, scale=1.5, seed=21).bfloat16()
+    out = torch.empty(B, N, D, dtype=torch.bfloat16, device="cuda")
+    ops.attention(qkv, qkv, qkv, B=B, H=H, Nq=N, Nk=N, q_col0=0, k_col0=D, v_col0=2 * D, scale=0.125, out=out)
+    for b in (0, 3, 5):
+        one = torch.empty(1, N, D, dtype=torch.bfloat16, device="cuda")
+        x = qkv[b:b + 1].contiguous()
+        ops.attention(x, x, x, B=1, H=H, Nq=N, Nk=N, q_col0=0, k_col0=D, v_col0=2 * D, scale=0.125, out=one)
+        assert torch.equal(one[0], out[b])
+    q, k, v = (t.float().view(B, N, H, 64).transpose(1, 2) for t in qkv.split(D, dim=-1))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, D)
+    assert rel_err(out, ref) < 1.5e-2
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("causal,Nq,Nk", [(False, 19, 19), (False, 19, 2049), (True, 22, 22), (False, 1, 300), (False, 19, 1025),
                                           (False, 5, 4100), (False, 1, 2049)])   # the long-key cases run key-split + combine
