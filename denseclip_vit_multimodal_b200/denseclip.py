@@ -14,6 +14,7 @@ NCHW fp32 tensors are only materialised when a caller asks for them through the 
 from __future__ import annotations
 
 import logging
+import os
 
 import torch
 import torch.nn as nn
@@ -23,6 +24,9 @@ from .heads import FCNHead, IdentityHead
 from .models import (CLIPTextContextEncoder, CLIPTextEncoder, CLIPVisionTransformer, ContextDecoder, ViTFeatureFusionNeck,
                      _f32, _param_versions, default_precision)
 from .utils import tokenize
+
+# run the score-map / ContextDecoder branch on a side stream, concurrently with the neck / heads branch (DCLIP_OVERLAP_TAIL=0: off)
+_OVERLAP_TAIL = os.environ.get("DCLIP_OVERLAP_TAIL", "1") != "0"
 
 logger = logging.getLogger(__name__)
 
@@ -385,8 +389,22 @@ class DenseCLIP(nn.Module):
             tokens, _ = ops.nchw_to_tokens(last_nchw, row_off=1, rows=1 + gh * gw)
         else:
             tokens = enc["last_tokens"]
-        # 2. score map / context decoder: computed as the reference does, though forward() never returns it
-        text, score, _ = self._tail_native(tokens, gh, gw)
+        # 2. score map / context decoder: computed as the reference does, though forward() never returns it.
+        #    The branch (vis/global projection, ContextDecoder, score map: ~50 mostly latency-bound launches) shares nothing
+        #    with the neck / heads branch below, so it runs on a side stream and the two overlap (also inside a captured
+        #    graph, where the fork/join become graph dependencies).  DCLIP_OVERLAP_TAIL=0 runs them back to back.
+        side = self._tail_stream(img.device) if _OVERLAP_TAIL else None
+        if side is not None:
+            main = torch.cuda.current_stream(img.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                text, score, _ = self._tail_native(tokens, gh, gw)
+                join = torch.cuda.Event()
+                join.record(side)
+        else:
+            text, score, _ = self._tail_native(tokens, gh, gw)
         self.last_text_embeddings, self.last_score_map = text, score
         # 3. neck
         if self.neck is not None:
@@ -407,9 +425,20 @@ class DenseCLIP(nn.Module):
             gt = gt_semantic_seg if gt_semantic_seg is not None else kwargs.get('gt_depth', kwargs.get('depth_targets', kwargs.get('seg_targets')))
             out_hw = tuple(gt.shape[-2:]) if gt is not None else (gh, gw)
             seg, depth = self._heads_native(feat_b, gh, gw, out_hw)
+            if side is not None:
+                main.wait_event(join)
             return {'main_output': seg, 'depth_output': depth, 'aux_losses': {}}
         seg, depth = self._heads_native(feat_b, gh, gw, tuple(img.shape[2:]), class_map=bool(kwargs.get('_class_map', False)))
+        if side is not None:
+            main.wait_event(join)  # the score map / text embeddings are complete when forward() returns, as before
         return {'seg': seg, 'depth': depth}
+
+    def _tail_stream(self, device):
+        st = getattr(self, "_tail_side_stream", None)
+        if st is None or st.device != torch.device(device):
+            st = torch.cuda.Stream(device=device)
+            self._tail_side_stream = st
+        return st
 
     # ---- inference helpers (reference denseclip.py:938-1041) ----
     def inference(self, img, img_meta, rescale):
