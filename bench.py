@@ -31,7 +31,7 @@ ENCODER_FLOPS_PER_IMAGE = 505.25e9          # patch 2.416 + QKV 87.
 ATTN_FLOPS_PER_IMAGE_LAYER = 154.770e9 / 12  # QK^T + PV, 12 heads x 2049^2 x 64 x 2 x 2
 # measured on this pool's B200s by the driver (MEASURED_PEAKS.json at the time of writing); re-read from the file if present
 RECORDED_PEAKS = {"hbm_gbs": 6541.8, "bf16_tflops": 1674.0, "bf16_tflops_sustained": 1403.8}
-ATTN_DRAM_TRAFFIC_BYTES = 239.1e6           # profiles/r01_attn_ncu_persistent.txt (ncu --set full): dram read 207.7 MB + write 31.4 MB per launch (B=16)
+ATTN_DRAM_TRAFFIC_BYTES = 236.0e6           # profiles/r01_attn_ncu_persistent.txt (ncu --set full): dram read 203.9 MB + write 32.1 MB per launch (B=16)
 
 
 def peaks():
