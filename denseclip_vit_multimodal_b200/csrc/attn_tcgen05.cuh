@@ -975,7 +975,6 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   const int first_r = G_CTAS - 1 - cta;
   const int n_items = (n_reg - first_r + G_CTAS - 1) / G_CTAS;
   const int G = n_items * T;                      // KV tiles this CTA processes per query tile
-  const bool Nk_ge8 = true;                       // (host enables tail_overlap only for Nk >= 32)
 
   // ---- tail rows first (whole CTA, plain loads, shared memory not yet in use) ----
   for (int t = cta; t < n_tail && !p.tail_overlap; t += G_CTAS) {
@@ -1047,7 +1046,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       }
     } else if (warp >= 10) {
       // ------------------------------- tail rows in the background ----------------
-      if (p.tail_overlap && Nk_ge8) {
+      if (p.tail_overlap) {  // (the host enables it only for Nk >= 32: every key group sees a valid key in its first trip)
         float* s_merge = reinterpret_cast<float*>(smem + Cfg::BAR_OFF + 256);
         for (int t = cta; t < n_tail; t += G_CTAS) {
           const int h = t % p.H, b = t / p.H;
