@@ -1029,14 +1029,14 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           const int qb = r % nqb_reg, h = (r / nqb_reg) % p.H, b = r / (nqb_reg * p.H);
           const int q_row0 = p.q_start + qb * 2 * Cfg::TQ;
           const int qbuf = n & 1;
-          if (n >= 2) mbar_wait(&q_empty[qbuf], ((n >> 1) - 1) & 1);
+          if (n >= 2) mbar_wait_relaxed(&q_empty[qbuf], ((n >> 1) - 1) & 1);
           mbar_arrive_expect_tx(&q_full[qbuf], 2 * 16384);
           tma_load_3d(smem + Cfg::Q_OFF + qbuf * 32768, &tmQ, &q_full[qbuf], p.q_col0 + h * Cfg::HD, q_row0, b);
           tma_load_3d(smem + Cfg::Q_OFF + qbuf * 32768 + 16384, &tmQ, &q_full[qbuf], p.q_col0 + h * Cfg::HD, q_row0 + Cfg::TQ, b);
           for (int j = 0; j < T; ++j, ++g) {
             const int s = g % Cfg::KV_STAGES;
             const uint32_t ph = (g / Cfg::KV_STAGES) & 1;
-            mbar_wait(&kv_empty[s], ph ^ 1);
+            mbar_wait_relaxed(&kv_empty[s], ph ^ 1);
             mbar_arrive_expect_tx(&k_full[s], 16384);
             tma_load_3d(smem + Cfg::K_OFF + s * 16384, &tmK, &k_full[s], p.k_col0 + h * Cfg::HD, koff + j * Cfg::TKV, b);
             mbar_arrive_expect_tx(&v_full[s], 16384);

@@ -92,6 +92,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait for a producer that runs several stages ahead: back off between probes so the single polling lane does not take
+// issue slots (and power) from the math warps of its sub-partition (ncu: 12.5 k try_wait executions per CTA otherwise).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(256);
+    if (++spins > (1u << 24)) {  // ~4 s
+      printf("dclip: mbarrier wait timeout (producer) block=%d bar=%u parity=%u\n", blockIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA loads (tile mode). Coordinates are innermost-first, in elements.
 // ---------------------------------------------------------------------------------------------
