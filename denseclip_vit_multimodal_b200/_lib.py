@@ -102,7 +102,8 @@ class VitOutputs(C.Structure):
 
 EXPORTS = [
     "dclip_abi_version", "dclip_create", "dclip_destroy", "dclip_last_error", "dclip_launch_count",
-    "dclip_reset_launch_count", "dclip_gemm", "dclip_layernorm", "dclip_cast_bf16", "dclip_attention",
+    "dclip_reset_launch_count", "dclip_gemm", "dclip_sizeof_gemm_args", "dclip_layernorm", "dclip_cast_bf16", "dclip_attention",
+    "dclip_attention_split",
     "dclip_attention_small", "dclip_im2col_patches", "dclip_posemb_interp", "dclip_tap_nchw", "dclip_nchw_to_tokens",
     "dclip_token_mean", "dclip_score_map", "dclip_upsample_bilinear", "dclip_upsample_argmax", "dclip_eval_stats", "dclip_gamma_residual", "dclip_conv3x3_gather",
     "dclip_vit_create", "dclip_vit_destroy", "dclip_vit_set_weights", "dclip_vit_workspace_bytes", "dclip_vit_forward",
@@ -127,6 +128,8 @@ def _declare(lib):
     lib.dclip_layernorm.argtypes = [vp, vp, ll, vp, vp, f, i, i, vp, ll, vp, ll, i, ll, vp]
     lib.dclip_cast_bf16.argtypes = [vp, vp, ll, vp, ll, i, i, i, ll, f, vp]
     lib.dclip_attention.argtypes = [vp, vp, vp, vp, ll, ll, ll, ll, ll, ll, i, i, i, i, i, i, i, i, f, vp, ll, ll, vp]
+    lib.dclip_attention_split.argtypes = [vp, vp, vp, vp, ll, ll, ll, ll, ll, ll, i, i, i, ll, i, i, i, i, f, vp, ll, ll, ll, vp]
+    lib.dclip_sizeof_gemm_args.argtypes = []
     lib.dclip_attention_small.argtypes = [vp, vp, vp, vp, i, ll, ll, ll, ll, ll, ll, i, i, i, i, i, i, i, i, f, i, vp, i, ll, ll,
                                           ll, vp]
     lib.dclip_im2col_patches.argtypes = [vp, vp, i, i, i, i, vp, ll, i, ll, vp]
@@ -147,8 +150,9 @@ def _declare(lib):
     lib.dclip_vit_forward.argtypes = [vp, vp, i, i, i, vp, C.c_size_t, C.POINTER(VitOutputs), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("dclip_last_error", "dclip_launch_count"):
+        if name not in ("dclip_last_error", "dclip_launch_count", "dclip_sizeof_gemm_args"):
             fn.restype = i
+    lib.dclip_sizeof_gemm_args.restype = C.c_size_t
 
 
 def lib():
@@ -166,6 +170,8 @@ def lib():
                 _declare(loaded)
                 if loaded.dclip_abi_version() != 1:
                     raise DclipError("libdenseclip_b200.so ABI version mismatch; rebuild")
+                if loaded.dclip_sizeof_gemm_args() != C.sizeof(GemmArgs):
+                    raise DclipError("dclip_gemm_args layout mismatch between _lib.GemmArgs and the library; rebuild")
                 _lib = loaded
     return _lib
 

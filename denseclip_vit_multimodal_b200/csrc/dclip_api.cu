@@ -19,7 +19,8 @@ struct dclip_handle_s {
   // plan caches: tensor maps are encoded once per distinct argument set
   std::map<std::string, GemmPlan> gemm_plans;
   std::map<std::string, AttnPlan> attn_plans;
-  AttnSmallScratch attn_small_scratch;  // key-split partials (one buffer per handle: calls on one handle must not overlap across streams)
+  std::map<std::string, AttnSplitPlan> attn_split_plans;
+  std::map<void*, AttnSmallScratch> attn_small_scratch;  // key-split partials, one per stream (never freed before destroy)
 };
 
 struct dclip_vit_s {
@@ -29,22 +30,30 @@ struct dclip_vit_s {
 
 static thread_local std::string g_create_err;
 
+// Runs f with the handle's device current and RESTORES the caller's device afterwards (the host framework's notion of
+// the current device must not change behind its back).
 template <class F>
 static int guarded(dclip_handle_t h, F&& f) {
+  int cur = -1;
+  bool switched = false;
+  int rc = 0;
   try {
     if (!h) throw Error{"null handle"};
-    int cur = -1;
     DCLIP_CHECK_CUDA(cudaGetDevice(&cur));
-    if (cur != h->device) DCLIP_CHECK_CUDA(cudaSetDevice(h->device));
+    if (cur != h->device) {
+      DCLIP_CHECK_CUDA(cudaSetDevice(h->device));
+      switched = true;
+    }
     f();
-    return 0;
   } catch (const Error& e) {
     if (h) h->err = e.msg; else g_create_err = e.msg;
-    return 1;
+    rc = 1;
   } catch (const std::exception& e) {
     if (h) h->err = e.what(); else g_create_err = e.what();
-    return 2;
+    rc = 2;
   }
+  if (switched) cudaSetDevice(cur);
+  return rc;
 }
 
 template <class T>
@@ -60,6 +69,7 @@ static void check_launch(dclip_handle_t h, int n = 1) {
 extern "C" {
 
 int dclip_abi_version(void) { return DCLIP_ABI_VERSION; }
+size_t dclip_sizeof_gemm_args(void) { return sizeof(dclip_gemm_args); }
 
 int dclip_create(int device, dclip_handle_t* out) {
   try {
@@ -76,8 +86,11 @@ int dclip_create(int device, dclip_handle_t* out) {
                prop.major, prop.minor);
       throw Error{buf};
     }
+    int cur = 0;
+    DCLIP_CHECK_CUDA(cudaGetDevice(&cur));
     DCLIP_CHECK_CUDA(cudaSetDevice(device));
     get_encode_fn();
+    DCLIP_CHECK_CUDA(cudaSetDevice(cur));
     auto* h = new dclip_handle_s;
     h->device = device;
     *out = h;
@@ -89,7 +102,13 @@ int dclip_create(int device, dclip_handle_t* out) {
 }
 
 int dclip_destroy(dclip_handle_t h) {
-  if (h && h->attn_small_scratch.ptr) cudaFree(h->attn_small_scratch.ptr);
+  if (h) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(h->device);
+    for (auto& kv : h->attn_small_scratch) kv.second.release();
+    cudaSetDevice(cur);
+  }
   delete h;
   return 0;
 }
@@ -158,9 +177,13 @@ int dclip_attention(dclip_handle_t h, const void* q, const void* k, const void* 
                     int B, int H, int Nq, int q_start, int Nk, float scale, void* out, long long ldo, long long out_bs,
                     void* stream) {
   return guarded(h, [&] {
-    AttnOperands op{static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v),
-                    int(ldq), int(ldk), int(ldv), q_bs, k_bs, v_bs, Nq};
-    AttnParams p{};
+    // the plan-cache key is the raw bytes of (op, p): zero them first so the padding bytes are deterministic
+    AttnOperands op;
+    memset(&op, 0, sizeof(op));
+    op.q = static_cast<const __nv_bfloat16*>(q); op.k = static_cast<const __nv_bfloat16*>(k); op.v = static_cast<const __nv_bfloat16*>(v);
+    op.ldq = int(ldq); op.ldk = int(ldk); op.ldv = int(ldv); op.q_bs = q_bs; op.k_bs = k_bs; op.v_bs = v_bs; op.Nq_total = Nq;
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
     p.B = B; p.H = H; p.Nq_total = Nq; p.q_start = q_start; p.Nk = Nk;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.scale_log2 = scale * 1.4426950408889634f;
@@ -189,7 +212,33 @@ int dclip_attention_small(dclip_handle_t h, const void* q, const void* k, const 
     const int align = is_f32 ? 4 : 8;
     DCLIP_REQUIRE(ldk % align == 0 && ldv % align == 0 && k_col0 % align == 0 && v_col0 % align == 0 && k_bs % align == 0 &&
                       v_bs % align == 0, "small attention: K/V rows must be 16B aligned");
-    h->launches += run_attn_small(p, static_cast<cudaStream_t>(stream), &h->attn_small_scratch);
+    h->launches += run_attn_small(p, static_cast<cudaStream_t>(stream), &h->attn_small_scratch[stream]);
+  });
+}
+
+int dclip_attention_split(dclip_handle_t h, const void* q, const void* k, const void* v, long long ldq, long long ldk,
+                          long long ldv, long long q_bs, long long k_bs, long long v_bs, int q_col0, int k_col0, int v_col0,
+                          long long lo_off, int B, int H, int Nq, int Nk, float scale, void* out, long long ldo, long long out_bs,
+                          long long out_lo_off, void* stream) {
+  return guarded(h, [&] {
+    AttnSplitOperands op;
+    memset(&op, 0, sizeof(op));
+    op.q = static_cast<const __nv_bfloat16*>(q); op.k = static_cast<const __nv_bfloat16*>(k); op.v = static_cast<const __nv_bfloat16*>(v);
+    op.ldq = int(ldq); op.ldk = int(ldk); op.ldv = int(ldv); op.q_bs = q_bs; op.k_bs = k_bs; op.v_bs = v_bs;
+    AttnSplitParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0; p.lo_off = int(lo_off);
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.out = static_cast<__nv_bfloat16*>(out); p.out_bs = out_bs; p.ldo = int(ldo); p.out_lo_off = int(out_lo_off);
+    const std::string key = key_of(op) + key_of(p);
+    auto it = h->attn_split_plans.find(key);
+    if (it == h->attn_split_plans.end()) {
+      if (h->attn_split_plans.size() > 1024) h->attn_split_plans.clear();
+      it = h->attn_split_plans.emplace(key, make_attn_split_plan(op, p)).first;
+    }
+    run_attn_split(it->second, static_cast<cudaStream_t>(stream));
+    h->launches += 1;
   });
 }
 

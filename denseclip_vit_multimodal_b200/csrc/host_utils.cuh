@@ -12,6 +12,11 @@
 #include <mutex>
 #include <string>
 
+#include <map>
+#include <utility>
+#include <vector>
+
+#include "attn_split_tcgen05.cuh"
 #include "attn_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 
@@ -93,14 +98,28 @@ inline CUtensorMap make_tmap_2d_bf16(const void* base, uint64_t rows, uint64_t c
   return make_tmap_bf16(base, 2, dims, str, box);
 }
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs through several handles)
 inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of the function: opt in once per (kernel, device)
+template <class Kern>
+inline void ensure_dyn_smem(Kern kern, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  DCLIP_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_pair(reinterpret_cast<const void*>(kern), dev);
+  if (done.count(key)) return;
+  DCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert(key);
 }
 
 struct GemmOperands {
@@ -128,12 +147,8 @@ struct GemmPlan {
 template <int BN, int ACT, int FLAGS, bool PAIR = false>
 inline void launch_gemm_inst(const GemmPlan& plan, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, PAIR>;
-  static bool attr_set = false;
   auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, FLAGS, PAIR>;
-  if (!attr_set) {
-    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  ensure_dyn_smem(kern, Cfg::SMEM_BYTES);
   if (PAIR) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(plan.grid);
@@ -209,6 +224,10 @@ inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
       if (p.act == ACT_NONE && flags == EPI_OUT_F32) return launch_gemm_inst<BN, ACT_NONE, EPI_OUT_F32, true>(plan, stream);
       if (p.act == ACT_NONE && flags == (EPI_RESID | EPI_OUT_F32 | EPI_REMAP))  // patch embedding (+ positional embedding, row remap)
         return launch_gemm_inst<BN, ACT_NONE, EPI_RESID | EPI_OUT_F32 | EPI_REMAP, true>(plan, stream);
+      // fp32-class path (3-pass split products): fused QKV and c_fc write bf16 hi | lo
+      if (p.act == ACT_NONE && flags == (EPI_OUT_BF16 | EPI_SPLIT)) return launch_gemm_inst<BN, ACT_NONE, EPI_OUT_BF16 | EPI_SPLIT, true>(plan, stream);
+      if (p.act == ACT_QUICKGELU_PRECISE && flags == (EPI_OUT_BF16 | EPI_SPLIT))
+        return launch_gemm_inst<BN, ACT_QUICKGELU_PRECISE, EPI_OUT_BF16 | EPI_SPLIT, true>(plan, stream);
       trace_generic_gemm(BN, p.act, flags, 1, p);
       return launch_gemm_generic<BN, true>(plan, stream);
     }
@@ -230,6 +249,7 @@ inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
   if (p.act == ACT_RELU && flags == (EPI_OUT_F32 | EPI_OUT_BF16)) return launch_gemm_inst<BN, ACT_RELU, EPI_OUT_F32 | EPI_OUT_BF16>(plan, stream);
   if (p.act == ACT_RELU && flags == EPI_OUT_F32) return launch_gemm_inst<BN, ACT_RELU, EPI_OUT_F32>(plan, stream);
   // split-precision MLP hidden layers: ContextDecoder (erf GELU) and text tower (exact QuickGELU), bf16 hi|lo output
+  if (p.act == ACT_NONE && flags == (EPI_OUT_BF16 | EPI_SPLIT)) return launch_gemm_inst<BN, ACT_NONE, EPI_OUT_BF16 | EPI_SPLIT>(plan, stream);
   if (p.act == ACT_GELU_ERF && flags == (EPI_OUT_BF16 | EPI_SPLIT)) return launch_gemm_inst<BN, ACT_GELU_ERF, EPI_OUT_BF16 | EPI_SPLIT>(plan, stream);
   if (p.act == ACT_QUICKGELU_PRECISE && flags == (EPI_OUT_BF16 | EPI_SPLIT))
     return launch_gemm_inst<BN, ACT_QUICKGELU_PRECISE, EPI_OUT_BF16 | EPI_SPLIT>(plan, stream);
@@ -392,11 +412,7 @@ inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
 template <bool PT, int POLY, int MODE>
 inline void run_attn_variant(const AttnPlan& plan, cudaStream_t stream) {
   using Cfg = AttnCfgT<PT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<PT, POLY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  ensure_dyn_smem(attn_fwd_tcgen05_kernel<PT, POLY, MODE>, Cfg::SMEM_BYTES);
   attn_fwd_tcgen05_kernel<PT, POLY, MODE><<<plan.grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.tmO, plan.p);
   DCLIP_CHECK_CUDA(cudaGetLastError());
 }
@@ -404,11 +420,7 @@ inline void run_attn_variant(const AttnPlan& plan, cudaStream_t stream) {
 template <int POLY>
 inline void run_attn_persistent(const AttnPlan& plan, int grid, cudaStream_t stream) {
   using Cfg = AttnPersistCfg;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_persistent_kernel<POLY, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  ensure_dyn_smem(attn_fwd_persistent_kernel<POLY, 0>, Cfg::SMEM_BYTES);
   attn_fwd_persistent_kernel<POLY, 0><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.tmO, plan.p);
   DCLIP_CHECK_CUDA(cudaGetLastError());
 }
@@ -458,10 +470,52 @@ inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
   }
 }
 
-// scratch for the key-split partials: grown on demand (dclip_api.cu keeps one buffer per handle)
+// ---- fp32-class (hi|lo split) tensor-core attention ------------------------------------------------------------
+struct AttnSplitPlan {
+  CUtensorMap tmQ, tmK, tmV;
+  AttnSplitParams p;
+  int grid = 0;
+};
+
+struct AttnSplitOperands {
+  const __nv_bfloat16 *q, *k, *v;  // token-major [B][N][ld], each row holding hi and (lo_off columns further) lo halves
+  int ldq, ldk, ldv;
+  long long q_bs, k_bs, v_bs;
+};
+
+inline AttnSplitPlan make_attn_split_plan(const AttnSplitOperands& op, const AttnSplitParams& p) {
+  DCLIP_REQUIRE(p.B > 0 && p.H > 0 && p.Nk > 0 && p.Nq > 0, "bad attention shape");
+  DCLIP_REQUIRE(p.ldo % 8 == 0 && p.out_lo_off % 8 == 0 && p.out_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0,
+                "split attention out alignment");
+  DCLIP_REQUIRE(op.ldq % 8 == 0 && op.ldk % 8 == 0 && op.ldv % 8 == 0 && p.q_col0 % 8 == 0 && p.k_col0 % 8 == 0 && p.v_col0 % 8 == 0 &&
+                p.lo_off % 8 == 0 && op.q_bs % 8 == 0 && op.k_bs % 8 == 0 && op.v_bs % 8 == 0, "split attention operand alignment");
+  AttnSplitPlan plan;
+  plan.p = p;
+  plan.tmQ = make_tmap_tokens_bf16(op.q, p.B, p.Nq, op.ldq, op.q_bs);
+  plan.tmK = make_tmap_tokens_bf16(op.k, p.B, p.Nk, op.ldk, op.k_bs);
+  plan.tmV = make_tmap_tokens_bf16(op.v, p.B, p.Nk, op.ldv, op.v_bs);
+  plan.grid = ((p.Nq + 255) / 256) * p.H * p.B;
+  return plan;
+}
+
+inline void run_attn_split(const AttnSplitPlan& plan, cudaStream_t stream) {
+  ensure_dyn_smem(attn_fwd_split_kernel, AttnSplitCfg::SMEM_BYTES);
+  attn_fwd_split_kernel<<<plan.grid, AttnSplitCfg::THREADS, AttnSplitCfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.p);
+  DCLIP_CHECK_CUDA(cudaGetLastError());
+}
+
+// scratch for the key-split partials: grown on demand.  dclip_api.cu keeps one per (handle, stream), so calls on
+// different streams never share a buffer.  A block that has been handed to a launch is NEVER freed before the handle is
+// destroyed: a captured CUDA graph may have its address baked in (growing allocates a new block and retires the old one).
 struct AttnSmallScratch {
   float* ptr = nullptr;
   size_t bytes = 0;
+  std::vector<float*> retired;
+  void release() {
+    if (ptr) cudaFree(ptr);
+    for (float* r : retired) cudaFree(r);
+    ptr = nullptr; bytes = 0; retired.clear();
+  }
 };
 
 template <int QB>
@@ -483,7 +537,7 @@ inline int launch_attn_small(SmallAttnParams p, cudaStream_t stream, AttnSmallSc
       cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
       DCLIP_CHECK_CUDA(cudaStreamIsCapturing(stream, &cs));
       DCLIP_REQUIRE(cs == cudaStreamCaptureStatusNone, "small attention: scratch must be sized by an eager warm-up call before graph capture");
-      if (scratch->ptr) DCLIP_CHECK_CUDA(cudaFree(scratch->ptr));
+      if (scratch->ptr) scratch->retired.push_back(scratch->ptr);  // (kept alive: graphs captured earlier still point at it)
       scratch->ptr = nullptr; scratch->bytes = 0;
       DCLIP_CHECK_CUDA(cudaMalloc(&scratch->ptr, need));
       scratch->bytes = need;
@@ -500,11 +554,7 @@ inline int launch_attn_small(SmallAttnParams p, cudaStream_t stream, AttnSmallSc
     if (smem > 200 * 1024) return launch_attn_small<8>(p, stream, scratch);  // (key splitting disabled: scores of 20 queries do not fit)
   }
   DCLIP_REQUIRE(smem <= 200 * 1024, "small attention: Nk=%d too large for the smem score buffer", p.Nk);
-  static bool attr = false;
-  if (!attr) {
-    DCLIP_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  ensure_dyn_smem(attn_small_kernel<QB>, 200 * 1024);
   attn_small_kernel<QB><<<ctas * S, 256, smem, stream>>>(p);
   DCLIP_CHECK_CUDA(cudaGetLastError());
   if (S > 1) {

@@ -3,7 +3,7 @@
 // Data layout in HBM (token-major, B images flattened into M = B * Ntok rows; Ntok = 1 + gh*gw, CLS at row 0):
 //   x     fp32 [M, D]        residual stream, never rounded to bf16
 //   h     bf16 [M, D*s]      LayerNorm output / attention output (A operand of the next GEMM), s = 2 in precise mode (hi|lo)
-//   qkv   bf16 [M, 3D]       fused in_proj output, head-interleaved columns [q | k | v]   (precise: fp32 [M, 3D])
+//   qkv   bf16 [M, 3D]       fused in_proj output, head-interleaved columns [q | k | v]   (precise: bf16 [M, 6D] = hi | lo)
 //   g     bf16 [M, 4D*s]     QuickGELU(c_fc) output; the patch im2col matrix aliases it before layer 0
 //   pos   fp32 [Ntok, D]     positional embedding interpolated to (gh, gw)
 //   lnp   fp32 [M, D]        ln_post output (only when the last layer is tapped)
@@ -16,87 +16,6 @@
 #include "rowwise.cuh"
 
 namespace dclip {
-
-// fp32 CUDA-core flash attention for the precise ("fp32") path: one thread per query row, K/V tiles broadcast
-// from shared memory.  qkv fp32 [B][N][3D]; writes bf16 hi|lo split rows [M, 2D] for the split-bf16 out-proj GEMM.
-__global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int N,
-                                                      int D, float scale) {
-  __shared__ float4 Ks[32][16];
-  __shared__ float4 Vs[32][16];
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int qi = blockIdx.x * 128 + threadIdx.x;
-  const long long ld = 3LL * D;
-  const float* base = qkv + (long long)b * N * ld;
-  float q[64], o[64];
-  const bool active = qi < N;
-  {
-    const float4* qp = reinterpret_cast<const float4*>(base + (long long)(active ? qi : 0) * ld + h * 64);
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      const float4 t = qp[d];
-      q[4 * d] = t.x * scale; q[4 * d + 1] = t.y * scale; q[4 * d + 2] = t.z * scale; q[4 * d + 3] = t.w * scale;
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < 64; ++d) o[d] = 0.f;
-  float m = -INFINITY, l = 0.f;
-  for (int k0 = 0; k0 < N; k0 += 32) {
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = threadIdx.x + 128 * i;  // 512 float4 per tile
-      const int j = idx >> 4, d4 = idx & 15;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (k0 + j < N) {
-        kv = *reinterpret_cast<const float4*>(base + (long long)(k0 + j) * ld + D + h * 64 + 4 * d4);
-        vv = *reinterpret_cast<const float4*>(base + (long long)(k0 + j) * ld + 2 * D + h * 64 + 4 * d4);
-      }
-      Ks[j][d4] = kv;
-      Vs[j][d4] = vv;
-    }
-    __syncthreads();
-    float s[32];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int d = 0; d < 16; d += 2) {
-        const float4 k0v = Ks[j][d], k1v = Ks[j][d + 1];
-        a0 += q[4 * d] * k0v.x + q[4 * d + 1] * k0v.y + q[4 * d + 2] * k0v.z + q[4 * d + 3] * k0v.w;
-        a1 += q[4 * d + 4] * k1v.x + q[4 * d + 5] * k1v.y + q[4 * d + 6] * k1v.z + q[4 * d + 7] * k1v.w;
-      }
-      s[j] = (k0 + j < N) ? a0 + a1 : -INFINITY;
-      mx = fmaxf(mx, s[j]);
-    }
-    const float m_new = fmaxf(m, mx);
-    const float alpha = expf(m - m_new);
-    l *= alpha;
-#pragma unroll
-    for (int d = 0; d < 64; ++d) o[d] *= alpha;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float pj = expf(s[j] - m_new);
-      l += pj;
-#pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        const float4 vv = Vs[j][d];
-        o[4 * d] += pj * vv.x; o[4 * d + 1] += pj * vv.y; o[4 * d + 2] += pj * vv.z; o[4 * d + 3] += pj * vv.w;
-      }
-    }
-    m = m_new;
-  }
-  if (!active) return;
-  const float inv = 1.f / l;
-  __nv_bfloat16* orow = out + ((long long)b * N + qi) * (2LL * D) + h * 64;
-#pragma unroll
-  for (int d = 0; d < 64; d += 2) {
-    const float a = o[d] * inv, c = o[d + 1] * inv;
-    const uint32_t hi = pack_bf16x2(a, c);
-    *reinterpret_cast<uint32_t*>(orow + d) = hi;
-    *reinterpret_cast<uint32_t*>(orow + D + d) = pack_bf16x2(a - __uint_as_float(hi << 16), c - __uint_as_float(hi & 0xffff0000u));
-  }
-}
 
 struct VitConfig {
   int width = 768, layers = 12, heads = 12, patch = 16, grid0 = 14, precise = 0;
@@ -209,8 +128,7 @@ class VitEncoder {
       launch_layernorm(l1, st); ++n;
       run_gemm(layer_plans_[li].qkv, st); ++n;
       if (cfg.precise) {
-        dim3 grid((L.Ntok + 127) / 128, cfg.heads, B);
-        attn_f32_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(w8 + L.qkv), hbuf, L.Ntok, D, 0.125f); ++n;
+        run_attn_split(attn_split_plan_, st); ++n;   // 3-pass hi|lo tensor-core attention, writes hbuf as hi | lo
       } else {
         run_attn(attn_plan_, st); ++n;
         if (attn_plan_.p.q_start == 1) { run_attn_small(cls_attn_, st); ++n; }
@@ -284,6 +202,7 @@ class VitEncoder {
   GemmPlan patch_plan_;
   std::vector<LayerPlans> layer_plans_;
   AttnPlan attn_plan_;
+  AttnSplitPlan attn_split_plan_;
   SmallAttnParams cls_attn_;
 
   void build_plans(int B, int H, int W, void* ws, const Layout& L) {
@@ -313,8 +232,9 @@ class VitEncoder {
         GemmOperands op{hbuf, D * s, lw.in_proj_w, D * s};
         GemmParams p{};
         p.M = M; p.N = 3 * D; p.K = D; p.split_in = cfg.precise; p.bias = lw.in_proj_b; p.out_scale = 1.f;
-        if (cfg.precise) { p.out_f32 = reinterpret_cast<float*>(w8 + L.qkv); p.ldc = 3 * D; }
-        else { p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(w8 + L.qkv); p.ldcb = 3 * D; }
+        p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(w8 + L.qkv);
+        if (cfg.precise) { p.ldcb = 6 * D; p.split_out = 1; p.split_out_off = 3 * D; }   // [q k v]_hi | [q k v]_lo
+        else p.ldcb = 3 * D;
         lp.qkv = make_gemm_plan(op, p);
       }
       {
@@ -340,7 +260,17 @@ class VitEncoder {
         lp.proj = make_gemm_plan(op, p);
       }
     }
-    if (!cfg.precise) {
+    if (cfg.precise) {
+      const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(w8 + L.qkv);
+      const long long bs = (long long)L.Ntok * 6 * D;
+      AttnSplitOperands op{qkv, qkv, qkv, 6 * D, 6 * D, 6 * D, bs, bs, bs};
+      AttnSplitParams p{};
+      p.B = B; p.H = cfg.heads; p.Nq = L.Ntok; p.Nk = L.Ntok;
+      p.q_col0 = 0; p.k_col0 = D; p.v_col0 = 2 * D; p.lo_off = 3 * D;
+      p.scale_log2 = 0.125f * 1.4426950408889634f;
+      p.out = hbuf; p.out_bs = (long long)L.Ntok * 2 * D; p.ldo = 2 * D; p.out_lo_off = D;
+      attn_split_plan_ = make_attn_split_plan(op, p);
+    } else {
       const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(w8 + L.qkv);
       const long long bs = (long long)L.Ntok * 3 * D;
       AttnOperands op{qkv, qkv, qkv, 3 * D, 3 * D, 3 * D, bs, bs, bs, L.Ntok};

@@ -300,12 +300,16 @@ class DenseCLIP(nn.Module):
         B, _, gh, gw = vis.shape
         tokens, _ = ops.nchw_to_tokens(vis, row_off=1, rows=1 + gh * gw, f32=True, bf16=False)
         text, score, _ = self._tail_native(tokens, gh, gw)
-        x_orig = list(x)
-        feats = list(x)
+        # denseclip.py:586 clones the inputs and :678 binds features_for_head to that SAME list, so the 2nd and 4th return
+        # values are one object and both carry the score-map concat at score_concat_index (copies are layout, not compute)
+        x_orig = [f.clone() for f in x]
+        feats = x_orig
         if 0 <= self.score_concat_index < len(feats):
             tgt = feats[self.score_concat_index]
             sm = score if score.shape[2:] == tgt.shape[2:] else ops.upsample_bilinear(score, tuple(tgt.shape[2:]))
             feats[self.score_concat_index] = torch.cat([tgt, sm], dim=1)  # layout only
+        elif self.score_concat_index != -1:
+            logger.warning("score_concat_index %s invalid. Score map not concatenated.", self.score_concat_index)
         return text, feats, score, x_orig
 
     # ---- forward ----
@@ -339,6 +343,7 @@ class DenseCLIP(nn.Module):
         cost of the ~190 kernels of one step.  Outputs are then STATIC buffers, overwritten by the next call."""
         self._use_graph = bool(flag)
         self._graphs = {}
+        self._max_graphs = 4
         return self
 
     def _graph_forward(self, img, class_map: bool):
@@ -360,17 +365,36 @@ class DenseCLIP(nn.Module):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self._forward_impl(static_in, None, False, {'_class_map': class_map})
-            ent = dict(ver=ver, graph=graph, inp=static_in, out=out, launches=_lib.launch_count(dev) - n0)
-            self._graphs = {key: ent}  # one live graph: its private pool holds a full set of activations
+            ent = dict(ver=ver, graph=graph, inp=static_in, out=out, launches=_lib.launch_count(dev) - n0,
+                       keep=getattr(self, "_last_workspace", None))
+            # a few live graphs (each private pool holds a full set of activations): alternating forward()/predict() or two
+            # input shapes must not re-capture on every call; the oldest entry goes first
+            self._graphs[key] = ent
+            while len(self._graphs) > self._max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+        else:
+            self._graphs[key] = self._graphs.pop(key)  # mark as most recently used
         ent["inp"].copy_(img, non_blocking=True)
         ent["graph"].replay()
         self.graph_launches_per_step = ent["launches"]
         return ent["out"]
 
     def forward(self, img, img_metas=None, gt_semantic_seg=None, return_loss=True, **kwargs):
-        if getattr(self, "_use_graph", False) and not (return_loss and self.training) and img.is_cuda:
-            return self._graph_forward(img, bool(kwargs.get('_class_map', False)))
-        return self._forward_impl(img, gt_semantic_seg, return_loss, kwargs)
+        """Reference denseclip.py:702-916.  Error contract (denseclip.py:738-752, 802-817): the reference catches every
+        exception of a stage, logs it and returns ``None`` outputs.  That behaviour is kept for MODEL-LEVEL errors (bad
+        shapes, inconsistent configuration: ValueError / TypeError / AttributeError / KeyError / IndexError), so the
+        reference's callers see the same dict.  A failure of the NATIVE layer (``DclipError``: missing extension, no sm_100
+        device, CPU tensor, kernel launch error) or any CUDA runtime error is never swallowed -- it propagates, because a
+        silent ``None`` there would hide a broken accelerator path."""
+        try:
+            if getattr(self, "_use_graph", False) and not (return_loss and self.training) and img.is_cuda:
+                return self._graph_forward(img, bool(kwargs.get('_class_map', False)))
+            return self._forward_impl(img, gt_semantic_seg, return_loss, kwargs)
+        except (ValueError, TypeError, AttributeError, KeyError, IndexError) as e:
+            logger.error("Error during DenseCLIP forward: %s", e, exc_info=True)
+            if return_loss and self.training:
+                return {'main_output': None, 'depth_output': None, 'aux_losses': {}}
+            return {'seg': None, 'depth': None}
 
     def _forward_impl(self, img, gt_semantic_seg, return_loss, kwargs):
         """Reference denseclip.py:702-916.  Inference returns {'seg': [B,K,H,W], 'depth': [B,1,H,W]} fp32; the training
@@ -383,6 +407,7 @@ class DenseCLIP(nn.Module):
         enc = self.backbone.forward_native(img, taps_nchw=not use_tokens, taps_tokens_bf16=use_tokens, last_tokens=True)
         gh, gw = enc["grid"]
         B = img.shape[0]
+        self._last_workspace = enc["workspace"]   # (a captured graph holds on to it, see _graph_forward)
         if self.backbone.out_indices[-1] != self.backbone.layers - 1:
             # x[-1] is then an intermediate (un-normalised) tap: rebuild its token view from the NCHW tap
             last_nchw = enc["nchw"][-1] if enc["nchw"] else ops.tap_nchw(enc["tokens_bf16"][-1].float(), gh, gw)

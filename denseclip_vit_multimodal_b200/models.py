@@ -5,8 +5,8 @@ interchangeable, but ``forward`` runs the hand-written sm_100a kernels behind th
 ``nn.Module`` tree only *owns parameters*; no torch compute op runs on the forward path, and there is no CPU fallback.
 
 Precision: ``precision="bf16"`` (default) is the tensor-core path (bf16 operands, fp32 accumulation, fp32 residual
-stream and LayerNorm/softmax statistics); ``precision="fp32"`` switches the GEMMs to a three-pass split-bf16 product
-(hi*hi + lo*hi + hi*lo, ~2^-16 relative error) and attention to an fp32 CUDA-core kernel.
+stream and LayerNorm/softmax statistics); ``precision="fp32"`` is the fp32-class path: every GEMM and both attention
+products run as three-pass split-bf16 tensor-core products (hi*hi + lo*hi + hi*lo, ~2^-16 relative error), softmax in fp32.
 """
 from __future__ import annotations
 
@@ -289,7 +289,11 @@ class CLIPVisionTransformer(nn.Module):
         if ws is None:
             nbytes = C.c_size_t()
             _lib.check(st["h"], _lib.lib().dclip_vit_workspace_bytes(st["vit"], B, H, W, C.byref(nbytes)))
-            st["ws"].clear()
+            # a few workspaces stay cached (alternating input shapes); a captured CUDA graph keeps its own reference to the
+            # one it was recorded with (returned as "workspace"), so dropping the oldest entry here never frees memory a
+            # live graph still writes to
+            while len(st["ws"]) >= 4:
+                st["ws"].pop(next(iter(st["ws"])))
             ws = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=x.device)
             st["ws"][key] = ws
         ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
@@ -311,7 +315,7 @@ class CLIPVisionTransformer(nn.Module):
         stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         _lib.check(st["h"], _lib.lib().dclip_vit_forward(st["vit"], C.c_void_p(x.data_ptr()), B, H, W, C.c_void_p(ws_ptr),
                                                           C.c_size_t(nbytes_of(ws, ws_ptr)), C.byref(o), stream))
-        return dict(nchw=nchw, tokens_bf16=tok, tokens_bf16_stacked=tok_all, last_tokens=last, grid=(gh, gw))
+        return dict(nchw=nchw, tokens_bf16=tok, tokens_bf16_stacked=tok_all, last_tokens=last, grid=(gh, gw), workspace=ws)
 
     def forward(self, x: torch.Tensor):
         """[B,3,H,W] -> list of fp32 [B, width, H//ps, W//ps], one per out_index (reference models.py:543-597)."""

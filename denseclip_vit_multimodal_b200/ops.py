@@ -147,6 +147,19 @@ def attention(qkv_q, qkv_k, qkv_v, *, B, H, Nq, Nk, q_col0, k_col0, v_col0, scal
     return out
 
 
+def attention_split(qkv_q, qkv_k, qkv_v, *, B, H, Nq, Nk, q_col0, k_col0, v_col0, lo_off, scale, out, out_lo_off):
+    """fp32-class tensor-core flash attention (head_dim 64): operands are bf16 [B, N, ld] views whose rows hold a hi half at
+    column col0 + 64h and the matching lo half ``lo_off`` columns further; three tcgen05 passes per product, fp32 softmax.
+    ``out`` bf16 [B, Nq, ldo]: hi at column 64h, lo at ``out_lo_off`` + 64h."""
+    for t in (qkv_q, qkv_k, qkv_v, out):
+        _req(t, torch.bfloat16, "attention operand")
+        assert t.dim() == 3
+    _call(qkv_q, _lib.lib().dclip_attention_split, _ptr(qkv_q), _ptr(qkv_k), _ptr(qkv_v), qkv_q.stride(1), qkv_k.stride(1),
+          qkv_v.stride(1), qkv_q.stride(0), qkv_k.stride(0), qkv_v.stride(0), q_col0, k_col0, v_col0, lo_off, B, H, Nq, Nk,
+          float(scale), _ptr(out), out.stride(1), out.stride(0), out_lo_off, _stream(qkv_q))
+    return out
+
+
 def attention_small(q, k, v, *, B, H, q_first, q_count, Nk, q_col0, k_col0, v_col0, scale, out, causal=False,
                     out_split_off=0):
     """fp32 CUDA-core attention for a handful of query rows. q/k/v: [B, N, ld] fp32 or bf16 (all the same dtype)."""

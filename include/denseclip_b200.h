@@ -11,6 +11,7 @@
  *   dclip_gemm                nn.Linear / in_proj / out_proj / 1x1 Conv2d          models.py:275-281,287-289; denseclip.py:198,616
  *   dclip_layernorm           LayerNorm (fp32 stats, eps 1e-5)                     models.py:243-249
  *   dclip_attention           softmax(QK^T/sqrt(d))V inside nn.MultiheadAttention  models.py:287-289
+ *   dclip_attention_split     the same op in fp32-class precision (3-pass hi|lo split)  models.py:287-289
  *   dclip_attention_small     Attention.forward einsum/softmax/einsum (19 queries), causal text attention  models.py:328-344, 836-842
  *   dclip_im2col_patches      Conv2d(3,D,ps,stride=ps) operand gather               models.py:407,546-548
  *   dclip_posemb_interp       interpolate_pos_encoding                              models.py:514-540
@@ -77,6 +78,8 @@ typedef struct {
 } dclip_gemm_args;
 
 int dclip_gemm(dclip_handle_t h, const dclip_gemm_args* a, void* stream);
+/* sizeof(dclip_gemm_args) as compiled into the library: bindings check their struct mirror against it */
+size_t dclip_sizeof_gemm_args(void);
 
 /* ---- LayerNorm over the last dim; D % 128 == 0, D <= 1024 ----------------------------------------------------- */
 int dclip_layernorm(dclip_handle_t h, const float* x, long long ldx, const float* gamma, const float* beta, float eps,
@@ -94,6 +97,14 @@ int dclip_attention(dclip_handle_t h, const void* q, const void* k, const void* 
                     long long ldv, long long q_bs, long long k_bs, long long v_bs, int q_col0, int k_col0, int v_col0,
                     int B, int H, int Nq, int q_start, int Nk, float scale, void* out, long long ldo, long long out_bs,
                     void* stream);
+/* fp32-class tensor-core flash attention for precision="fp32" (same reference op, models.py:287-289): every operand row
+ * holds a bf16 hi half and, lo_off columns further, its lo half (x = hi + lo); S = QhKh + QlKh + QhKl and
+ * O = PhVh + PlVh + PhVl are three tcgen05 passes each, softmax in fp32.  out bf16 [B][Nq][ldo]: hi at column 64h,
+ * lo at out_lo_off + 64h (the hi|lo A operand of the split out-proj GEMM). */
+int dclip_attention_split(dclip_handle_t h, const void* q, const void* k, const void* v, long long ldq, long long ldk,
+                          long long ldv, long long q_bs, long long k_bs, long long v_bs, int q_col0, int k_col0, int v_col0,
+                          long long lo_off, int B, int H, int Nq, int Nk, float scale, void* out, long long ldo, long long out_bs,
+                          long long out_lo_off, void* stream);
 /* few-query fp32 attention on CUDA cores; inputs bf16 (is_f32 = 0) or fp32; rows [q_first, q_first + q_count) */
 int dclip_attention_small(dclip_handle_t h, const void* q, const void* k, const void* v, int is_f32, long long ldq,
                           long long ldk, long long ldv, long long q_bs, long long k_bs, long long v_bs, int q_col0,
@@ -137,7 +148,7 @@ int dclip_conv3x3_gather(dclip_handle_t h, const void* in, int in_f32, long long
 /* ---- CLIPVisionTransformer.forward ---------------------------------------------------------------------------- */
 typedef struct {
   int width, layers, heads, patch_size, grid0; /* grid0 = input_resolution / patch_size (stored pos-emb grid) */
-  int precise;                                 /* 0: bf16 tensor-core path; 1: split-bf16 GEMMs + fp32 attention */
+  int precise;                                 /* 0: bf16 tensor-core path; 1: fp32-class path (3-pass hi|lo split GEMMs and attention) */
 } dclip_vit_config;
 
 /* All weights stay owned by the caller and must outlive the object.  bf16 matrices are [out, in] row-major; in

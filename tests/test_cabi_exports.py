@@ -51,3 +51,25 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM"):   # tcgen05.mma, TMA load, tcgen05.ld / st
         assert mnemonic in sass, mnemonic
     assert "HMMA." not in sass.replace("UTCHMMA", "")           # no legacy mma.sync tensor path
+
+
+def test_gemm_args_mirrors_match_the_library():
+    """a binding whose struct mirror is shorter than dclip_gemm_args makes dclip_gemm read past it.  The
+    library exports sizeof(dclip_gemm_args); the package's mirror and the one printed in INTEGRATION.md must match it."""
+    from denseclip_vit_multimodal_b200 import _lib
+    lib = _lib.lib()                      # (lib() itself refuses to load on a mismatch)
+    assert ctypes.sizeof(_lib.GemmArgs) == lib.dclip_sizeof_gemm_args()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index("class GemmArgs(C.Structure)"):]
+    block = block[:block.index("]\n") + 1]
+    doc_fields = [(n, getattr(ctypes, t)) for n, t in re.findall(r'\("(\w+)", C\.(c_\w+)\)', block)]
+    assert doc_fields == list(_lib.GemmArgs._fields_)      # (ctypes aliases c_longlong to c_long on LP64: compare the types)
+    hdr = open(os.path.join(ROOT, "include", "denseclip_b200.h")).read()
+    body = hdr[hdr.index("typedef struct {"):hdr.index("} dclip_gemm_args;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.replace("typedef struct {", "").split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [re.sub(r"^.*[\s\*]", "", part.strip()) for part in decl.split(",")]
+    assert names == [n for n, _ in _lib.GemmArgs._fields_]

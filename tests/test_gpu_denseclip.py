@@ -45,7 +45,7 @@ def test_forward_matches_reference_golden(golden_cases, name, precision):
     else:
         assert float(np.abs(score.cpu().numpy() - g["score"]).max()) <= 2e-2   # north_star: bf16 max-abs on the score map
         for k, e in errs.items():
-            assert e <= 5e-2, (k, e)
+            assert e <= 2e-2, (k, e)
     # forward() also stashes what the reference computes and drops
     assert rel_err(model.last_score_map, score) < 1e-5
 
@@ -66,7 +66,7 @@ def test_patch14_ragged_grid_against_oracle(precision):
     with torch.no_grad():
         out = model(img.cuda(), return_loss=False)
         ref = O.denseclip_forward(sd, cfg, img, return_intermediates=True)
-    tol = 1e-3 if precision == "fp32" else 5e-2
+    tol = 1e-3 if precision == "fp32" else 2e-2
     assert out["seg"].shape == (2, 19, 50, 76)
     assert rel_err(out["seg"], ref["seg"]) <= tol and rel_err(out["depth"], ref["depth"]) <= tol
     assert float((model.last_score_map.cpu() - ref["score"]).abs().max()) <= (1e-4 if precision == "fp32" else 2e-2)

@@ -1,6 +1,6 @@
 """GPU, BASELINE-size shapes (ViT-B/16, 512x1024): size-independent properties of the native forward --
-batch independence / shard equality (bit-exact), determinism, fp32-path vs bf16-path agreement on the normalised
-score map (north_star tolerance 2e-2; argmax agreement is reported), CUDA-graph replay equality."""
+batch independence / shard equality (bit-exact), determinism, CUDA-graph replay equality (also with two live graphs),
+pipelined predictor equality.  Parity against the oracle at this size lives in tests/test_gpu_parity_baseline.py."""
 import copy
 
 import pytest
@@ -39,27 +39,6 @@ def test_batch_independence_determinism_and_shard_equality(models):
     assert full["seg"].shape == (3, 19, 512, 1024) and torch.isfinite(full["seg"]).all()
 
 
-def test_bf16_path_against_fp32_path_on_score_map(models):
-    m, m32 = models
-    g = torch.Generator(device="cuda").manual_seed(2)
-    img = torch.randn(2, 3, 512, 1024, device="cuda", generator=g)
-    with torch.no_grad():
-        o16 = m(img, return_loss=False); s16 = m.last_score_map.clone()
-        o32 = m32(img, return_loss=False); s32 = m32.last_score_map.clone()
-    assert float(s32.abs().max()) <= 1.0 + 1e-5                       # cosine similarities
-    max_abs = float((s16 - s32).abs().max())
-    agree = float((s16.argmax(1) == s32.argmax(1)).float().mean())
-    top2 = s32.topk(2, dim=1).values
-    gap = top2[:, 0] - top2[:, 1]
-    clear = gap > 4 * max_abs                                          # pixels whose fp32 top-2 gap exceeds the bf16 noise
-    agree_clear = float((s16.argmax(1) == s32.argmax(1))[clear].float().mean()) if clear.any() else 1.0
-    seg_agree = float((o16["seg"].argmax(1) == o32["seg"].argmax(1)).float().mean())
-    print(f"score-map bf16 vs fp32-path: max_abs={max_abs:.2e} argmax_agree={agree:.4f} "
-          f"agree_where_gap>4*err={agree_clear:.4f} ({float(clear.float().mean()):.3f} of pixels) seg_argmax_agree={seg_agree:.4f}")
-    assert max_abs <= 2e-2                                             # north_star bf16 tolerance on the normalised score map
-    assert agree_clear >= 0.999
-
-
 def test_cuda_graph_replay_matches_eager(models):
     m, _ = models
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -72,6 +51,12 @@ def test_cuda_graph_replay_matches_eager(models):
                 assert torch.equal(m(i, return_loss=False)["seg"], e)
             pm = m.predict(imgs[0])
             assert torch.equal(pm["seg"].long(), eager[0].argmax(1))
+            # forward() and predict() alternate without re-capturing: both graphs stay live
+            n_graphs = len(m._graphs)
+            ids = {k: id(v["graph"]) for k, v in m._graphs.items()}
+            assert torch.equal(m(imgs[1], return_loss=False)["seg"], eager[1])
+            assert torch.equal(m.predict(imgs[1])["seg"].long(), eager[1].argmax(1))
+            assert len(m._graphs) == n_graphs == 2 and ids == {k: id(v["graph"]) for k, v in m._graphs.items()}
         finally:
             m.enable_cuda_graph(False)
 

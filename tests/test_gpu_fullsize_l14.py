@@ -45,4 +45,4 @@ def test_vit_l14_fullsize_properties(models):
     rel_seg = float((full["seg"][:1] - o32["seg"]).abs().max() / o32["seg"].abs().max())
     print(f"ViT-L/14 bf16 vs fp32-path: score-map max_abs={max_abs:.2e} seg rel={rel_seg:.2e}")
     assert float(s32.abs().max()) <= 1.0 + 1e-5
-    assert max_abs <= 2e-2 and rel_seg <= 5e-2
+    assert max_abs <= 2e-2 and rel_seg <= 2e-2   # (parity against the ORACLE at this config: tests/test_gpu_parity_baseline.py)

@@ -244,3 +244,116 @@ def test_im2col_patches(ops, ps, H, W, split):
     assert torch.equal(got[:, :K], hi)
     if split:
         assert torch.equal(got[:, K:], (ref - hi.float()).bfloat16())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp32-class (hi|lo split) tensor-core attention: against an fp64 evaluation of softmax(QK^T/8)V on the SAME fp32 inputs.
+# (2, 12, 2049): the BASELINE ViT-B/16 sequence (17th KV tile holds one key, ninth query block one row); 2629: ViT-L/14.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,N", [(1, 1, 1), (2, 2, 129), (1, 2, 300), (2, 12, 2049), (1, 2, 2629), (1, 3, 257)])
+def test_attention_split_is_fp32_class(ops, B, H, N):
+    D = H * 64
+    qkv = _rand(B, N, 3 * D, scale=1.5, seed=31)
+    sp = ops.split_bf16(qkv.view(B * N, 3 * D)).view(B, N, 6 * D)            # [q k v]_hi | [q k v]_lo
+    out = torch.empty(B, N, 2 * D, dtype=torch.bfloat16, device="cuda")
+    ops.attention_split(sp, sp, sp, B=B, H=H, Nq=N, Nk=N, q_col0=0, k_col0=D, v_col0=2 * D, lo_off=3 * D, scale=0.125, out=out,
+                        out_lo_off=D)
+    got = out[..., :D].float() + out[..., D:].float()
+    q, k, v = (t.double().view(B, N, H, 64).transpose(1, 2) for t in qkv.split(D, dim=-1))
+    ref = (torch.softmax(q @ k.transpose(2, 3) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(B, N, D).float()
+    assert torch.isfinite(got).all()
+    assert rel_err(got, ref) < 5e-5      # hi+lo operands carry 16 mantissa bits (2^-17 = 7.6e-6 each), ex2.approx 2^-22
+    tail = N % 256
+    if tail:
+        assert rel_err(got[:, N - tail:], ref[:, N - tail:]) < 5e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Production tile paths at the BASELINE shape M = 16 x 2049 = 32784 rows: CTA-pair (cta_group::2) 256x256 tiles, the
+# 256x192 residual tile, the TMA-store epilogue, the second bf16 output (feature tap) and the patch-embed row remap.
+# None of these is reached by the small shapes above (pair mode needs >= 148 pair units).
+# ---------------------------------------------------------------------------------------------------------------------
+M_PROD = 16 * 2049
+
+
+@pytest.mark.parametrize("N,K,act", [(2304, 768, None), (3072, 768, "quickgelu")])
+def test_gemm_production_tma_store_pair(ops, N, K, act):
+    a, w, b = _rand(M_PROD, K, seed=41).bfloat16(), _rand(N, K, scale=K ** -0.5, seed=42).bfloat16(), _rand(N, seed=43)
+    _, ob = ops.gemm(a, w, bias=b, act=act, want_bf16=True)
+    for r0 in (0, 16000, M_PROD - 1200):    # fp32 reference in row slabs (the full [M, N] fp32 product is 400 MB)
+        ref = a[r0:r0 + 1200].float() @ w.float().t() + b
+        if act:
+            ref = ref * torch.sigmoid(1.702 * ref)
+        assert rel_err(ob[r0:r0 + 1200], ref) < 1.2e-2
+
+
+@pytest.mark.parametrize("K,tap", [(768, False), (3072, False), (3072, True)])
+def test_gemm_production_residual_pair_and_bn192(ops, K, tap):
+    """out-proj (K = 768 -> 256x192 pair tiles) and c_proj (K = 3072 -> 256x256 pair tiles, optional bf16 tap output):
+    fp32 residual stream updated in place."""
+    N = 768
+    a, w, b = _rand(M_PROD, K, seed=44).bfloat16(), _rand(N, K, scale=K ** -0.5, seed=45).bfloat16(), _rand(N, seed=46)
+    x = _rand(M_PROD, N, seed=47)
+    x0 = x.clone()
+    tap_out = torch.empty(M_PROD, N, dtype=torch.bfloat16, device="cuda") if tap else None
+    ops.gemm(a, w, bias=b, residual=x, out_f32=x, out_bf16=tap_out)
+    ref = a.float() @ w.float().t() + b + x0
+    assert rel_err(x, ref) < 2e-5
+    if tap:
+        assert rel_err(tap_out, ref) < 1e-2
+        assert torch.equal(tap_out, x.bfloat16())      # the tap is exactly the rounded residual stream
+
+
+def test_gemm_production_patch_embed_remap(ops):
+    """patch rows m = b*P + p -> token rows b*Ntok + 1 + p, + positional embedding row 1 + p (models.py:546-556)."""
+    Bb, P, Nt, D, K = 16, 2048, 2049, 768, 768
+    a, w = _rand(Bb * P, K, seed=48).bfloat16(), _rand(D, K, scale=K ** -0.5, seed=49).bfloat16()
+    pos = _rand(Nt, D, seed=50)
+    x = torch.zeros(Bb * Nt, D, device="cuda")
+    from denseclip_vit_multimodal_b200 import _lib
+    import ctypes as C
+    g = _lib.GemmArgs()
+    g.A, g.lda, g.W, g.ldw = a.data_ptr(), K, w.data_ptr(), K
+    g.M, g.N, g.K, g.out_scale = Bb * P, D, K, 1.0
+    g.residual, g.ldr, g.res_mod, g.remap_P, g.remap_Nt = pos.data_ptr(), D, 1, P, Nt
+    g.out_f32, g.ldc = x.data_ptr(), D
+    ops._call(a, _lib.lib().dclip_gemm, C.byref(g), ops._stream(a))
+    ref = (a.float() @ w.float().t()).view(Bb, P, D) + pos[1:]
+    got = x.view(Bb, Nt, D)
+    assert rel_err(got[:, 1:], ref) < 2e-5
+    assert float(got[:, 0].abs().max()) == 0.0          # CLS rows are not touched by the GEMM
+
+
+def test_gemm_production_split_qkv(ops):
+    """fp32-class fused QKV at the production shape: 3-pass split product, bf16 hi|lo output (pair tiles)."""
+    M, N, K = 8 * 2049, 2304, 768
+    a, w, b = _rand(M, K, seed=51), _rand(N, K, scale=K ** -0.5, seed=52), _rand(N, seed=53)
+    _, o = ops.gemm(ops.split_bf16(a), ops.split_bf16(w), split_in=True, bias=b, want_bf16=True, split_out=True)
+    for r0 in (0, M - 900):
+        ref = (a[r0:r0 + 900].double() @ w.double().t() + b.double()).float()
+        assert rel_err(o[r0:r0 + 900, :N].float() + o[r0:r0 + 900, N:].float(), ref) < 3e-5
+
+
+def test_two_streams_small_attention_scratch_is_per_stream(ops):
+    """the key-split scratch of the few-query attention is per (handle, stream) and never freed while the
+    handle lives: two streams running different problem sizes concurrently must not disturb each other."""
+    B, H, D = 4, 4, 256
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    q1, kv1 = _rand(B, 19, D, seed=61), _rand(B, 2049, 2 * D, seed=62)
+    q2, kv2 = _rand(2 * B, 19, D, seed=63), _rand(2 * B, 4097, 2 * D, seed=64)
+    o1 = torch.empty(B, 19, D, device="cuda")
+    o2 = torch.empty(2 * B, 19, D, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            ops.attention_small(q1, kv1, kv1, B=B, H=H, q_first=0, q_count=19, Nk=2049, q_col0=0, k_col0=0, v_col0=D, scale=0.125, out=o1)
+        with torch.cuda.stream(s2):
+            ops.attention_small(q2, kv2, kv2, B=2 * B, H=H, q_first=0, q_count=19, Nk=4097, q_col0=0, k_col0=0, v_col0=D, scale=0.125, out=o2)
+    torch.cuda.synchronize()
+    for q, kv, o, n in ((q1, kv1, o1, 2049), (q2, kv2, o2, 4097)):
+        bb = q.shape[0]
+        qq = q.view(bb, 19, H, 64).transpose(1, 2)
+        kk = kv[..., :D].reshape(bb, n, H, 64).transpose(1, 2)
+        vv = kv[..., D:].reshape(bb, n, H, 64).transpose(1, 2)
+        ref = F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2).reshape(bb, 19, D)
+        assert rel_err(o, ref) < 2e-5
