@@ -27,11 +27,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "images/sec DenseCLIP ViT-B/16 fwd @512x1024"
-ENCODER_FLOPS_PER_IMAGE = 505.25e9          # patch 2.416 + QKV 87.016 + out 29.005 + MLP 232.041 + attn 154.770 GF
-ATTN_FLOPS_PER_IMAGE_LAYER = 154.770e9 / 12  # QK^T + PV, 12 heads x 2049^2 x 64 x 2 x 2
+# Algorithmic FLOPs per image at 512x1024; attention = QK^T + PV = heads x N^2 x 64 x 2 x 2 per layer
+MODELS = {
+    # ViT-B/16: patch 2.416 + QKV 87.016 + out 29.005 + MLP 232.041 + attention 154.770 GF; N = 2049 tokens
+    "vit_b16": dict(label="ViT-B/16", encoder_flops=505.25e9, attn_flops_layer=154.770e9 / 12, width=768, heads=12, patch=16, layers=12),
+    # ViT-L/14 (BASELINE configs[3], models.py:384-396): 3.165 + 396.966 + 132.322 + 1058.575 + 679.442 GF; N = 2629 tokens
+    "vit_l14": dict(label="ViT-L/14", encoder_flops=2270.47e9, attn_flops_layer=679.442e9 / 24, width=1024, heads=16, patch=14, layers=24),
+}
 # measured on this pool's B200s by the driver (MEASURED_PEAKS.json at the time of writing); re-read from the file if present
 RECORDED_PEAKS = {"hbm_gbs": 6541.8, "bf16_tflops": 1674.0, "bf16_tflops_sustained": 1403.8}
-ATTN_DRAM_TRAFFIC_BYTES = 236.0e6           # profiles/r01_attn_ncu_persistent.txt (ncu --set full): dram read 203.9 MB + write 32.1 MB per launch (B=16)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the shipped attention kernel at the default workload
+# (ViT-B/16, B = 16), from the ncu --set full capture committed under profiles/ (see ATTN_TRAFFIC_SOURCE); None = not captured
+ATTN_DRAM_TRAFFIC_BYTES = None
+ATTN_TRAFFIC_SOURCE = None
 
 
 def peaks():
@@ -42,8 +50,14 @@ def peaks():
     return dict(RECORDED_PEAKS), "MEASURED_PEAKS.json values recorded in bench.py (file not shipped to this box)"
 
 
-def model_kwargs(decoder_layers=3):
-    """The live yaml model (configs/denseclip_cityscapes.yaml:18-72) + the canonical 3-layer ContextDecoder."""
+def model_kwargs(decoder_layers=3, model="vit_b16"):
+    """The live yaml model (configs/denseclip_cityscapes.yaml:18-72) + the canonical 3-layer ContextDecoder (SURVEY N6);
+    model="vit_l14" swaps in the ViT-L/14 backbone of BASELINE configs[3] (models.py:384-396, one tap at layer 23)."""
+    if model == "vit_l14":
+        kw = model_kwargs(decoder_layers)
+        kw["backbone"] = dict(type='CLIPVisionTransformer', patch_size=14, width=1024, layers=24, heads=16, input_resolution=224,
+                              output_dim=1024, out_indices=[23])
+        return kw
     classes = ['road', 'sidewalk', 'building', 'wall', 'fence', 'pole', 'traffic light', 'traffic sign', 'vegetation', 'terrain',
                'sky', 'person', 'rider', 'car', 'truck', 'bus', 'train', 'motorcycle', 'bicycle']
     return dict(
@@ -131,9 +145,9 @@ def run_reference(args, rank):
     from oracle import denseclip_oracle as O  # the only place besides cpu_baseline where bench.py executes oracle/
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    cfg = O.model_config("vit_b16", 3)
+    cfg = O.model_config(args.model, 3)
     import denseclip_vit_multimodal_b200 as D
-    model = D.DenseCLIP(**copy.deepcopy(model_kwargs()))
+    model = D.DenseCLIP(**copy.deepcopy(model_kwargs(model=args.model)))
     init_uninitialised(model)
     sd = {k: v.detach().float() for k, v in model.state_dict().items()}
     img = O.synthetic_images(1, args.height, args.width, seed=0)
@@ -145,9 +159,10 @@ def run_reference(args, rank):
             O.denseclip_forward(sd, cfg, img)
         dt = time.perf_counter() - t0
     val = args.steps / dt
-    sample = f"{args.steps} forwards of 1 synthetic {args.height}x{args.width} image, fp32, torch CPU ({threads} threads)"
+    sample = (f"{args.steps} forwards of 1 synthetic {args.height}x{args.width} image, fp32, torch CPU ({threads} threads); every forward "
+              f"recomputes the 63.6 GF text tower as the reference does (the GPU arm caches it per weight version, SURVEY a10)")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args), "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample": sample},
@@ -156,9 +171,15 @@ def run_reference(args, rank):
         "gpu_launches": 0}))
 
 
+def metric_name(args):
+    return METRIC if args.model == "vit_b16" else METRIC.replace("ViT-B/16", MODELS[args.model]["label"])
+
+
 def workload_name(args):
-    return (f"DenseCLIP ViT-B/16 forward, batch {args.batch}/GPU @{args.height}x{args.width}, 19 classes, seg+depth heads, "
-            f"12-tap fusion neck, 3-layer ContextDecoder + score map (superset of BASELINE configs[1]); random init")
+    extra = "12-tap fusion neck" if args.model == "vit_b16" else "1-tap fusion neck (out_indices=[23])"
+    sup = " (superset of BASELINE configs[1])" if args.model == "vit_b16" else " (BASELINE configs[3])"
+    return (f"DenseCLIP {MODELS[args.model]['label']} forward, batch {args.batch}/GPU @{args.height}x{args.width}, 19 classes, seg+depth heads, "
+            f"{extra}, 3-layer ContextDecoder + score map{sup}; random init")
 
 
 def main():
@@ -167,6 +188,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--model", default="vit_b16", choices=sorted(MODELS), help="vit_b16 = BASELINE configs[1]/[2]; vit_l14 = configs[3] (use --batch 8)")
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--height", type=int, default=512)
     ap.add_argument("--width", type=int, default=1024)
@@ -180,10 +202,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank)
     args.warmup = max(args.warmup, 3)
+    spec = MODELS[args.model]
 
     import torch.distributed as dist
     import denseclip_vit_multimodal_b200 as D
     from denseclip_vit_multimodal_b200 import _lib, ops
+    from denseclip_vit_multimodal_b200 import distributed as dd
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200 GPU: the native path has no CPU fallback (use --impl reference for the CPU baseline)")
@@ -193,7 +217,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
-    model = D.DenseCLIP(**copy.deepcopy(model_kwargs()), precision=args.precision)
+    model = D.DenseCLIP(**copy.deepcopy(model_kwargs(model=args.model)), precision=args.precision)
     init_uninitialised(model)
     model = model.eval().to(dev)
     if not args.no_cuda_graph:
@@ -232,26 +256,66 @@ def main():
         launches = _lib.launch_count(local)
         if not args.no_cuda_graph:  # replays do not pass through the C ABI: count = kernels captured per step x steps
             launches = int(getattr(model, "graph_launches_per_step", 0)) * args.steps
-        ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        my_ms_step = e0.elapsed_time(e1) / args.steps
+        ms_step = max_over_ranks(my_ms_step)
         assert out["seg"].shape == (B, 19, H, W) and out["depth"].shape == (B, 1, H, W)
         del out
 
         # ---------------- encoder-only (the 60%-of-TC-peak target is quoted on the ViT encoder) ----------------
+        # one native call = ~90 launches; timed as a CUDA-graph replay like `value` (eager with --no-cuda-graph)
+        enc_call = lambda x: model.backbone.forward_native(x, taps_nchw=False, taps_tokens_bf16=True, last_tokens=True)  # noqa: E731
+        enc_in = dev_imgs[0].clone()
         for _ in range(2):
-            model.backbone.forward_native(dev_imgs[0], taps_nchw=False, taps_tokens_bf16=True, last_tokens=True)
+            enc_keep = enc_call(enc_in)
+        torch.cuda.synchronize()
+        enc_graph = None
+        if not args.no_cuda_graph:
+            enc_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(enc_graph):
+                enc_keep = enc_call(enc_in)
+        run_enc = (lambda: enc_graph.replay()) if enc_graph is not None else (lambda: enc_call(enc_in))
+        for _ in range(3):
+            run_enc()
         barrier()
         e0.record()
         for i in range(args.steps):
-            model.backbone.forward_native(dev_imgs[i % 2], taps_nchw=False, taps_tokens_bf16=True, last_tokens=True)
+            enc_in.copy_(dev_imgs[i % 2], non_blocking=True)   # alternate the two input batches, as `value` does
+            run_enc()
         e1.record()
         barrier()
-        enc_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        my_enc_ms = e0.elapsed_time(e1) / args.steps
+        enc_ms = max_over_ranks(my_enc_ms)
+        del enc_graph, enc_keep
 
         # ---------------- e2e: public API, pinned host buffers, H2D + D2H inside the timed region ----------------
         # PipelinedPredictor: every step copies that step's batch from pinned host memory and reads that step's result
         # (uint8 class map + fp32 depth) back to the host; copies of step i+1 / i-1 overlap the compute of step i.
+        # Multi-GPU (north star: "NCCL ... only to gather outputs and eval statistics"): EVERY step, on a side stream that
+        # waits for the step's results, the uint8 class maps of all shards are all-gathered and the step's evaluation
+        # statistics (19x19 confusion matrix + depth sum-sq-err / count, native kernel) are reduced with ONE all-reduce.
         from denseclip_vit_multimodal_b200.pipeline import PipelinedPredictor
         pipe = PipelinedPredictor(model, (B, 3, H, W), dev)
+        gt = torch.Generator(device="cpu").manual_seed(7 + rank)
+        tgt_seg = torch.randint(0, 20, (B, H, W), generator=gt).to(torch.uint8)
+        tgt_seg[tgt_seg == 19] = 255                                   # ~5% ignore_index pixels
+        tgt_seg = tgt_seg.to(dev)
+        tgt_depth = (torch.rand(B, 1, H, W, generator=gt) * 10).to(dev)
+        coll = {"stream": torch.cuda.Stream(device=dev), "n": 0, "packed": None,
+                "gathered": torch.empty(world * B, H, W, dtype=torch.uint8, device=dev) if world > 1 else None}
+
+        def post(slot):
+            with torch.cuda.stream(coll["stream"]):
+                coll["stream"].wait_event(pipe.ev_out[slot])
+                conf, ds = ops.eval_stats(pipe.seg_dev[slot], tgt_seg, 19, 255, pipe.depth_dev[slot], tgt_depth)
+                if world > 1:
+                    dist.all_gather_into_tensor(coll["gathered"], pipe.seg_dev[slot])
+                coll["packed"] = dd.reduce_eval_stats_packed(conf, ds)
+                coll["n"] += 1
+                ev = torch.cuda.Event()
+                ev.record(coll["stream"])
+            return ev
+
+        pipe.post = post
 
         def e2e_run(n):
             checksum = 0
@@ -260,31 +324,48 @@ def main():
                     r = pipe.collect()
                     checksum += int(r["seg"][0, 0, 0])
                 pipe.submit(host_imgs[i % 2])
-                if world > 1 and i % 8 == 7:  # gather the class maps of all shards (the only collective on the path)
-                    gathered = torch.empty(world * B, H, W, dtype=torch.uint8, device=dev)
-                    dist.all_gather_into_tensor(gathered, pipe.seg_dev[i % pipe.depth])
             while pipe.n_collected < pipe.n_submitted:
                 r = pipe.collect()
                 checksum += int(r["seg"][0, 0, 0])
+            coll["stream"].synchronize()
             return checksum
 
         e2e_run(4)
         barrier()
+        n_coll0 = coll["n"]
         t0 = time.perf_counter()
         e2e_run(args.steps)
         torch.cuda.synchronize()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+        my_e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e_ms = max_over_ranks(my_e2e_ms)
         barrier()
+        collectives_per_step = (coll["n"] - n_coll0) / args.steps
+        # verify the collective path once: this rank's slice of the last gather == its own last class map, and the reduced
+        # confusion matrix counts every non-ignored pixel of every shard exactly once
+        last_slot = (pipe.n_submitted - 1) % pipe.depth
+        _, miou, acc, rmse = dd.unpack_eval_stats(coll["packed"], 19)
+        n_valid = torch.tensor([float((tgt_seg != 255).sum())], device=dev, dtype=torch.float64)
+        if world > 1:
+            assert torch.equal(coll["gathered"][rank * B:(rank + 1) * B], pipe.seg_dev[last_slot]), "gathered class maps differ from the local shard"
+            dist.all_reduce(n_valid)
+        assert abs(float(coll["packed"][:361].sum()) - float(n_valid)) < 0.5, "reduced confusion matrix does not count every valid pixel once"
         h2d = host_imgs[0].numel() * 4
         d2h = pipe.seg_host[0].numel() + pipe.depth_host[0].numel() * 4
 
         # ---------------- roofline: dominant kernel (flash attention) timed live, alone ----------------
-        Dm, Hh, Nt = 768, 12, (H // 16) * (W // 16) + 1
-        qkv = (torch.randn(B, Nt, 3 * Dm, device=dev) * 2).to(torch.bfloat16)
-        att = torch.empty(B, Nt, Dm, dtype=torch.bfloat16, device=dev)
-        q_start = 0
-        run_attn = lambda: ops.attention(qkv, qkv, qkv, B=B, H=Hh, Nq=Nt, Nk=Nt, q_col0=0, k_col0=Dm, v_col0=2 * Dm, scale=0.125,  # noqa: E731
-                                         out=att, q_start=q_start)
+        Dm, Hh, Nt = spec["width"], spec["heads"], (H // spec["patch"]) * (W // spec["patch"]) + 1
+        precise = args.precision == "fp32"
+        qkv = torch.randn(B, Nt, 3 * Dm, device=dev) * 2
+        if precise:
+            qkv = ops.split_bf16(qkv.view(B * Nt, 3 * Dm)).view(B, Nt, 6 * Dm)
+            att = torch.empty(B, Nt, 2 * Dm, dtype=torch.bfloat16, device=dev)
+            run_attn = lambda: ops.attention_split(qkv, qkv, qkv, B=B, H=Hh, Nq=Nt, Nk=Nt, q_col0=0, k_col0=Dm, v_col0=2 * Dm, lo_off=3 * Dm,  # noqa: E731
+                                                   scale=0.125, out=att, out_lo_off=Dm)
+        else:
+            qkv = qkv.to(torch.bfloat16)
+            att = torch.empty(B, Nt, Dm, dtype=torch.bfloat16, device=dev)
+            run_attn = lambda: ops.attention(qkv, qkv, qkv, B=B, H=Hh, Nq=Nt, Nk=Nt, q_col0=0, k_col0=Dm, v_col0=2 * Dm, scale=0.125,  # noqa: E731
+                                             out=att, q_start=0)
         for _ in range(10):  # the clock needs a few ms to settle after the copy-bound e2e phase
             run_attn()
         torch.cuda.synchronize()
@@ -300,9 +381,21 @@ def main():
         del qkv, att
 
     pk, pk_src = peaks()
-    attn_tflops = B * ATTN_FLOPS_PER_IMAGE_LAYER / (attn_ms * 1e-3) / 1e12
-    enc_tflops = B * ENCODER_FLOPS_PER_IMAGE / (enc_ms * 1e-3) / 1e12
+    attn_tflops = B * spec["attn_flops_layer"] / (attn_ms * 1e-3) / 1e12
+    enc_tflops = B * spec["encoder_flops"] / (enc_ms * 1e-3) / 1e12
     clocks = clk.summary()
+
+    # per-rank record (names the straggler): every rank's own step times and its clocks under load
+    mine = [float(rank), my_ms_step, my_enc_ms, my_e2e_ms, float(clocks["sm_mhz"] or 0), float(clocks["power_w"] or 0),
+            float(len([r for r in clocks["reasons"] if r != "sw_power_cap"]))]
+    if world > 1:
+        allr = [torch.zeros(len(mine), device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allr, torch.tensor(mine, device=dev, dtype=torch.float64))
+        per_rank = [[float(v) for v in t.tolist()] for t in allr]
+    else:
+        per_rank = [mine]
+    per_rank = [{"rank": int(r[0]), "ms_per_step": round(r[1], 4), "encoder_ms": round(r[2], 4), "e2e_ms_per_step": round(r[3], 4),
+                 "sm_mhz": r[4], "power_w": r[5], "thermal_or_hw_slowdown": bool(r[6])} for r in per_rank]
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -310,7 +403,7 @@ def main():
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
         sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
-        cfg = O.model_config("vit_b16", 3)
+        cfg = O.model_config(args.model, 3)
         img1 = host_imgs[0][:1].clone()
         with torch.no_grad():
             ref = O.denseclip_forward(sd, cfg, img1, return_intermediates=True)   # warm-up, also a live parity check
@@ -320,29 +413,48 @@ def main():
                 O.denseclip_forward(sd, cfg, img1)
             dt = (time.perf_counter() - t0) / n_cpu
             got = model(dev_imgs[0][:1], return_loss=False)
+            got_score = model.last_score_map.float().cpu()
         err = float((got["seg"].cpu() - ref["seg"]).abs().max() / ref["seg"].abs().max())
         cpu_baseline = {"value": 1.0 / dt, "unit": "images/s", "cores": threads, "kind": "port",
-                        "sample": f"{n_cpu} forwards of 1 image {H}x{W} (same model/weights), fp32 torch CPU after 1 warm-up",
-                        "seg_rel_err_native_vs_port": err}
+                        "sample": (f"{n_cpu} forwards of 1 image {H}x{W} (same model/weights), fp32 torch CPU after 1 warm-up; the CPU arm recomputes the "
+                                   f"text tower every forward (~20% of its time) as the reference does, the GPU arm caches it per weight version"),
+                        "seg_rel_err_native_vs_port": err,
+                        "score_map_max_abs_err_native_vs_port": float((got_score - ref["score"]).abs().max()),
+                        "score_map_argmax_agreement_native_vs_port": float((got_score.argmax(1) == ref["score"].argmax(1)).float().mean())}
 
     if rank == 0:
         total_imgs_per_s = world * B / (ms_step * 1e-3)
+        dtype = "bf16" if args.precision == "bf16" else "bf16x3-split (fp32-class: every product as 3 tensor-core passes over hi|lo operands)"
+        attn_kernel = ("attn_fwd_split_kernel (fp32-class tcgen05 flash attention)" if precise
+                       else "tcgen05 flash attention (persistent, one CTA per SM)")
         line = {
-            "metric": METRIC, "value": total_imgs_per_s, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args), "value": total_imgs_per_s, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "bf16x3-split (fp32-class)", "data": "synthetic",
+            "dtype": dtype, "data": "synthetic",
             "config": {"workload": workload_name(args), "cuda_graph": not args.no_cuda_graph, "global_batch": world * B, "image": [H, W], "parallelism": f"dp{world} (batch sharded by image)",
                        "l2": "no explicit flush: each step streams ~4 GB of activations per GPU (>> 126 MB L2) and alternates 2 input batches"},
             "clocks": clocks,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "PipelinedPredictor(DenseCLIP.predict): pinned host images in, uint8 class map + fp32 depth back on the host, every step; copies overlap compute (wall-clock timed)"},
+                    "api": ("PipelinedPredictor(DenseCLIP.predict) -- the deployable API: pinned host images in, uint8 class map + fp32 depth back on the host, "
+                            "every step; copies overlap compute (wall-clock timed).  The reference's forward() contract (fp32 logits, 40x the D2H bytes) is "
+                            "what `value` runs; predict() fuses the argmax into the upsample"),
+                    "collectives_per_step": collectives_per_step,
+                    "collectives": (f"per step on a side stream: native eval-statistics kernel + ONE all-reduce (363 x f64)"
+                                    + (f" + all-gather of the uint8 class maps ({world * B * H * W} B)" if world > 1 else " (single rank: no NCCL call)")
+                                    + "; gathered maps and the reduced confusion matrix verified after the run"),
+                    "eval_stats_last_step": {"mIoU": miou, "pixel_acc": acc, "depth_rmse": rmse}},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "attn_fwd_persistent_kernel (tcgen05 flash attention, one CTA per SM, 12 launches/step)", "bound": "tensor",
+            "roofline": {"kernel": f"{attn_kernel}, {spec['layers']} launches/step", "bound": "tensor",
                          "achieved": attn_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": attn_tflops / pk["bf16_tflops"],
-                         "traffic": ATTN_DRAM_TRAFFIC_BYTES * B / 16, "ms_per_launch": attn_ms, "peak_source": pk_src + " (burst: kernel timed alone)"},
-            "encoder": {"ms_per_step": enc_ms, "tflops": enc_tflops, "flops_per_image": ENCODER_FLOPS_PER_IMAGE,
+                         "traffic": (ATTN_DRAM_TRAFFIC_BYTES if (args.model == "vit_b16" and B == 16 and not precise) else None),
+                         "traffic_source": ATTN_TRAFFIC_SOURCE, "ms_per_launch": attn_ms,
+                         "flops_per_launch": B * spec["attn_flops_layer"] * (3 if precise else 1),
+                         "note": ("algorithmic FLOPs (one pass); the fp32-class kernel executes 3x that on the tensor pipe" if precise else None),
+                         "peak_source": pk_src + " (burst: kernel timed alone)"},
+            "encoder": {"ms_per_step": enc_ms, "tflops": enc_tflops, "flops_per_image": spec["encoder_flops"],
                         "frac_of_burst_peak": enc_tflops / pk["bf16_tflops"], "frac_of_sustained_peak": enc_tflops / pk["bf16_tflops_sustained"],
-                        "images_per_s": world * B / (enc_ms * 1e-3)},
+                        "images_per_s": world * B / (enc_ms * 1e-3), "timed_as": "eager native call" if args.no_cuda_graph else "CUDA-graph replay"},
+            "per_rank": per_rank,
         }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline

@@ -244,6 +244,7 @@ __device__ __forceinline__ void attn_softmax_tile(uint32_t tS, uint32_t tO, uint
   DCLIP_TL(if (dbg) dbg[3] = clock64();)
 }
 
+#ifdef DCLIP_EXPERIMENTS
 // Speculative-max variant of attn_softmax_tile for KV tiles j >= 1.  The serial chain of one warpgroup per tile
 // (barrier wait -> TMEM load -> row max -> PV-done wait -> exponentials -> publish) is longer than the SFU work of the two
 // warpgroups together, so the chain, not the SFU, sets the step time (profiles/r01_attention_notes.md).  Here the
@@ -366,6 +367,8 @@ __device__ __forceinline__ void attn_softmax_tile_spec(uint32_t tS, uint32_t tO,
   l += (a0 + a1) + (a2 + a3);
   DCLIP_TL(if (dbg) dbg[3] = clock64();)
 }
+
+#endif  // DCLIP_EXPERIMENTS
 
 // ---------------------------------------------------------------------------------------------------------
 // CUDA-core path for a query block that holds only a few valid rows (N = 2049 tokens = 8 x 256 + 1: without it the ninth
@@ -750,13 +753,17 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       long long* dbg = nullptr;
       DCLIP_TL(dbg = (p.dbg && blockIdx.x == p.dbg_cta && (warp & 3) == 0 && lane == 0) ? p.dbg + (i * 32 + j) * 8 : nullptr;)
       DCLIP_TL(if (dbg) dbg[0] = clock64();)
-      constexpr bool SPEC = (MODE & 1) != 0, DEFER = (MODE & 2) != 0;
+      constexpr bool DEFER = (MODE & 2) != 0;
+#ifdef DCLIP_EXPERIMENTS
+      constexpr bool SPEC = (MODE & 1) != 0;
       if (SPEC && j > 0) {
         if (valid > 32)
           attn_softmax_tile_spec<128, PT, POLY, DEFER>(tS, tO, tP, sProw, r, lane, valid, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
         else
           attn_softmax_tile_spec<32, PT, POLY, DEFER>(tS, tO, tP, sProw, r, lane, valid, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
-      } else if (valid > 32)
+      } else
+#endif
+      if (valid > 32)
         attn_softmax_tile<128, PT, POLY, DEFER>(tS, tO, tP, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
       else
         attn_softmax_tile<32, PT, POLY, DEFER>(tS, tO, tP, sProw, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], (j - 1) & 1, i, j + 1 == T, p.token_mode, dbg);
@@ -1149,7 +1156,6 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   } else {
     // ------------------------------- softmax warpgroups --------------------------
     setmaxnreg_inc<208>();
-    constexpr bool SPEC = (MODE & 1) != 0, DEFER = (MODE & 2) != 0;
     const int i = warp >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
@@ -1188,12 +1194,15 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           }
         }
         const uint32_t odp = (g - 1) & 1;
-        if (SPEC && j > 0) {
+#ifdef DCLIP_EXPERIMENTS
+        if ((MODE & 1) != 0 && j > 0) {
           if (valid > 32)
-            attn_softmax_tile_spec<128, PT, POLY, DEFER>(tS, tO, tP, nullptr, r, lane, valid, sc, m_used, l, &s_free[i], &o_done[i], odp, i, last_tile, p.token_mode, nullptr);
+            attn_softmax_tile_spec<128, PT, POLY, (MODE & 2) != 0>(tS, tO, tP, nullptr, r, lane, valid, sc, m_used, l, &s_free[i], &o_done[i], odp, i, last_tile, p.token_mode, nullptr);
           else
-            attn_softmax_tile_spec<32, PT, POLY, DEFER>(tS, tO, tP, nullptr, r, lane, valid, sc, m_used, l, &s_free[i], &o_done[i], odp, i, last_tile, p.token_mode, nullptr);
-        } else if (valid > 32)
+            attn_softmax_tile_spec<32, PT, POLY, (MODE & 2) != 0>(tS, tO, tP, nullptr, r, lane, valid, sc, m_used, l, &s_free[i], &o_done[i], odp, i, last_tile, p.token_mode, nullptr);
+        } else
+#endif
+        if (valid > 32)
           attn_softmax_tile<128, PT, POLY, false>(tS, tO, tP, nullptr, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], odp, i, last_tile, p.token_mode, dbg);
         else
           attn_softmax_tile<32, PT, POLY, false>(tS, tO, tP, nullptr, r, lane, valid, j == 0, sc, m_used, l, &s_free[i], &o_done[i], odp, i, last_tile, p.token_mode, dbg);

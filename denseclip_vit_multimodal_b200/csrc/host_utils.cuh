@@ -16,6 +16,9 @@
 #include <utility>
 #include <vector>
 
+#ifdef DCLIP_WITH_ATTN_P4   // round-2 experiment (scripts/experiments/, selftest builds only; measured slower: profiles/r02_attention_notes.md)
+#include "../../scripts/experiments/attn_p4_tcgen05.cuh"
+#endif
 #include "attn_split_tcgen05.cuh"
 #include "attn_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
@@ -122,6 +125,18 @@ inline void ensure_dyn_smem(Kern kern, int bytes) {
   done.insert(key);
 }
 
+// A/B knobs of the round-1 / round-2 experiments are read from the environment ONLY in selftest builds
+// (-DDCLIP_EXPERIMENTS); the shipped library compiles the measured-best setting in and contains no getenv.
+#ifdef DCLIP_EXPERIMENTS
+inline int env_knob(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#define DCLIP_KNOB(name, dflt) ([] { static const int v = ::dclip::env_knob(name, dflt); return v; }())
+#else
+#define DCLIP_KNOB(name, dflt) (dflt)
+#endif
+
 struct GemmOperands {
   const __nv_bfloat16* A;
   int lda;  // elements
@@ -170,8 +185,7 @@ inline void launch_gemm_inst(const GemmPlan& plan, cudaStream_t stream) {
 // DCLIP_GEMM_TRACE=1: print every (BLOCK_N, act, epilogue flags, pair) combination that falls through to the generic
 // runtime-checked epilogue, once -- those are ~1.5x slower per tile than a specialised instantiation
 inline void trace_generic_gemm(int bn, int act, int flags, int pair, const GemmParams& p) {
-  static const bool on = [] { const char* e = getenv("DCLIP_GEMM_TRACE"); return e && e[0] == '1'; }();
-  if (!on) return;
+  if (!DCLIP_KNOB("DCLIP_GEMM_TRACE", 0)) return;
   static std::set<long long> seen;
   const long long key = ((long long)bn << 32) | (act << 16) | (flags << 4) | pair;
   if (seen.insert(key).second)
@@ -269,19 +283,19 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
   if (p.out_bf16) DCLIP_REQUIRE(p.ldcb % 4 == 0 && p.split_out_off % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 7) == 0, "out_bf16 alignment");
   if (p.residual) DCLIP_REQUIRE(p.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0, "residual alignment");
   if (p.bias) DCLIP_REQUIRE((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "bias alignment");
-  static const int cluster_env = [] { const char* e = getenv("DCLIP_GEMM_CLUSTER"); return e ? atoi(e) : -1; }();
+  const int cluster_env = DCLIP_KNOB("DCLIP_GEMM_CLUSTER", -1);
   const int num_m_pairs = ((p.M + 127) / 128 + 1) / 2;
   if (bn == 0) {
     bn = p.N > 128 ? 256 : (p.N > 64 ? 128 : 64);
     // latency-bound tiny problems (the ContextDecoder's M = 304 rows): narrow tiles spread the W traffic and the epilogue
     // over 4x more CTAs (measured in a CUDA graph: 10.9 -> 7.2 us, 14.8 -> 8.7 us per launch)
-    static const bool no_small = [] { const char* e = getenv("DCLIP_GEMM_NO_SMALL_BN"); return e && e[0] == '1'; }();
+    const bool no_small = DCLIP_KNOB("DCLIP_GEMM_NO_SMALL_BN", 0) != 0;
     if (!no_small && p.conv_C == 0 && (long long)((p.M + 127) / 128) * ((p.N + 255) / 256) * 8 <= sm_count()) bn = 64;
     // wave quantisation of the CTA-pair grid: N = 768 with M = 32784 is 387 pair tiles of 256x256 on 74 pairs (6 waves, 87%
     // full) but 516 tiles of 256x192 (7 waves, 99.6% full).  Only the fp32-residual epilogues are instantiated at 192, and
     // only short-K GEMMs win (measured, B200: K = 768 0.062 -> 0.054 ms; K = 3072 0.136 -> 0.140 ms, the narrower tile
     // costs more operand traffic per MMA than the fuller last wave saves).
-    static const bool no192 = [] { const char* e = getenv("DCLIP_GEMM_NO_BN192"); return e && e[0] == '1'; }();
+    const bool no192 = DCLIP_KNOB("DCLIP_GEMM_NO_BN192", 0) != 0;
     if (bn == 256 && !no192 && cluster_env != 0 && p.K <= 1536 && p.N % 192 == 0 && p.conv_C == 0 && p.residual && p.out_f32 && !p.split_out && p.remap_P == 0) {
       const int pairs = sm_count() / 2;
       const long long u256 = (long long)num_m_pairs * ((p.N + 255) / 256), u192 = (long long)num_m_pairs * (p.N / 192);
@@ -320,7 +334,7 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
   plan.p.cluster = use_cluster ? 2 : 1;
   plan.tmB = make_tmap_2d_bf16(op.W, p.N, kcols, op.ldw, use_cluster ? bn / 2 : bn);
   memset(&plan.tmC, 0, sizeof(plan.tmC));
-  static const bool no_tma_store = [] { const char* e = getenv("DCLIP_GEMM_NO_TMA_STORE"); return e && e[0] == '1'; }();
+  const bool no_tma_store = DCLIP_KNOB("DCLIP_GEMM_NO_TMA_STORE", 0) != 0;
   if (!no_tma_store && bn != 192 && p.out_bf16 && !p.out_f32 && !p.residual && !p.split_out && p.remap_P == 0 && p.ldcb % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0 && (p.dbg_mode == 0 || p.dbg_mode == 5)) {
     uint64_t dims[2] = {uint64_t(p.N), uint64_t(p.M)};
@@ -386,15 +400,14 @@ inline AttnPlan make_attn_plan(const AttnOperands& op, const AttnParams& p) {
   DCLIP_REQUIRE(p.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && p.out_batch_stride % 8 == 0, "attention out alignment");
   AttnPlan plan;
   plan.p = p;
-  static const int token_env = [] { const char* e = getenv("DCLIP_ATTN_TOKEN"); return e ? atoi(e) : 1; }();
-  plan.p.token_mode = token_env;
-  static const int tail_env = [] { const char* e = getenv("DCLIP_ATTN_TAIL_ROWS"); return e ? atoi(e) : 4; }();
+  plan.p.token_mode = DCLIP_KNOB("DCLIP_ATTN_TOKEN", 1);
+  const int tail_env = DCLIP_KNOB("DCLIP_ATTN_TAIL_ROWS", 4);
   plan.p.q = op.q; plan.p.k = op.k; plan.p.v = op.v;
   plan.p.ldq = op.ldq; plan.p.ldk = op.ldk; plan.p.ldv = op.ldv;
   plan.p.q_bs = op.q_bs; plan.p.k_bs = op.k_bs; plan.p.v_bs = op.v_bs;
-  static const int tail_ov_env = [] { const char* e = getenv("DCLIP_ATTN_TAIL_OVERLAP"); return e ? atoi(e) : 1; }();
+  const int tail_ov_env = DCLIP_KNOB("DCLIP_ATTN_TAIL_OVERLAP", 1);
   plan.p.tail_overlap = (tail_ov_env && p.Nk >= 32) ? 1 : 0;  // (the online softmax of the background path assumes every key group sees a valid key in its first trip)
-  static const int peel_env = [] { const char* e = getenv("DCLIP_ATTN_PEEL"); return e ? atoi(e) : 1; }();
+  const int peel_env = DCLIP_KNOB("DCLIP_ATTN_PEEL", 1);
   plan.p.peel_key0 = (peel_env && p.Nk > Cfg128::TKV && (p.Nk - 1) % Cfg128::TKV == 0) ? peel_env : 0;  // 2: also L2 / early L1 prefetch of k_0, v_0
   // the CUDA-core tail path keeps one fp32 score per key in shared memory
   plan.p.tail_rows_max = (size_t(p.Nk) * 4 + 16384 <= size_t(AttnCfg::SMEM_BYTES)) ? tail_env : 0;
@@ -417,6 +430,16 @@ inline void run_attn_variant(const AttnPlan& plan, cudaStream_t stream) {
   DCLIP_CHECK_CUDA(cudaGetLastError());
 }
 
+#ifdef DCLIP_WITH_ATTN_P4
+template <int POLY>
+inline void run_attn_p4(const AttnPlan& plan, int grid, cudaStream_t stream) {
+  using Cfg = AttnP4Cfg;
+  ensure_dyn_smem(attn_fwd_p4_kernel<POLY>, Cfg::SMEM_BYTES);
+  attn_fwd_p4_kernel<POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.tmO, plan.p);
+  DCLIP_CHECK_CUDA(cudaGetLastError());
+}
+#endif
+
 template <int POLY>
 inline void run_attn_persistent(const AttnPlan& plan, int grid, cudaStream_t stream) {
   using Cfg = AttnPersistCfg;
@@ -425,6 +448,21 @@ inline void run_attn_persistent(const AttnPlan& plan, int grid, cudaStream_t str
   DCLIP_CHECK_CUDA(cudaGetLastError());
 }
 
+// Production dispatch: the persistent kernel (P in TMEM, MUFU token, background tail rows, peeled key 0) whenever there is
+// at least one regular 256-query block; the one-CTA-per-item kernel only serves launches without any (a handful of rows).
+// The variants measured slower in round 1 / 2 (speculative max, deferred P stores, P through shared memory, polynomial exp2,
+// the 4-warpgroup P4 structure) exist only in selftest builds (-DDCLIP_EXPERIMENTS): profiles/r01_attention_notes.md,
+// profiles/r02_attention_notes.md.
+#ifndef DCLIP_EXPERIMENTS
+inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
+  const AttnParams& q = plan.p;
+  const int nqb = (q.Nq_total - q.q_start + 255) / 256;
+  const int rows_last = q.Nq_total - q.q_start - (nqb - 1) * 256;
+  const int n_reg = q.B * q.H * (nqb - (rows_last <= q.tail_rows_max ? 1 : 0));
+  if (n_reg > 0) return run_attn_persistent<0>(plan, n_reg < sm_count() ? n_reg : sm_count(), stream);
+  return run_attn_variant<true, 0, 0>(plan, stream);
+}
+#else
 // Production variant: P in TMEM (TS MMA) + DCLIP_ATTN_POLY_DEFAULT of every 4 exp2 pairs on the FMA pipe.
 // A/B knobs (selftests only): DCLIP_ATTN_P_SMEM=1 (P through shared memory), DCLIP_ATTN_POLY=0|1|2.
 #ifndef DCLIP_ATTN_POLY_DEFAULT
@@ -453,6 +491,14 @@ inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
     const int n_reg = q.B * q.H * (nqb - (rows_last <= q.tail_rows_max ? 1 : 0));
     if (n_reg > 0) {
       const int grid = n_reg < sm_count() ? n_reg : sm_count();
+#ifdef DCLIP_WITH_ATTN_P4
+      static const int impl = [] { const char* e = getenv("DCLIP_ATTN_IMPL"); return e ? atoi(e) : 2; }();   // 4: P4 experiment, 2: persistent kernel
+      if (impl == 4 && q.tail_overlap) {
+        if (poly == 2) return run_attn_p4<2>(plan, grid, stream);
+        if (poly) return run_attn_p4<1>(plan, grid, stream);
+        return run_attn_p4<0>(plan, grid, stream);
+      }
+#endif
       if (poly) return run_attn_persistent<1>(plan, grid, stream);
       return run_attn_persistent<0>(plan, grid, stream);
     }
@@ -469,6 +515,8 @@ inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
     default: return run_attn_variant<true, 1, 3>(plan, stream);
   }
 }
+
+#endif  // DCLIP_EXPERIMENTS
 
 // ---- fp32-class (hi|lo split) tensor-core attention ------------------------------------------------------------
 struct AttnSplitPlan {
@@ -525,7 +573,7 @@ inline int launch_attn_small(SmallAttnParams p, cudaStream_t stream, AttnSmallSc
   // long key ranges with few (batch, head, query-block) CTAs -- the ContextDecoder cross attention: 19 queries over 2048
   // keys -- are split over the keys (flash-decoding style) so the K/V stream is spread over ~4 waves of CTAs
   int S = 1;
-  static const bool no_split = [] { const char* e = getenv("DCLIP_ATTN_SMALL_NO_SPLIT"); return e && e[0] == '1'; }();
+  const bool no_split = DCLIP_KNOB("DCLIP_ATTN_SMALL_NO_SPLIT", 0) != 0;
   if (scratch && !no_split && !p.causal && p.Nk >= 1024) {
     S = (4 * sm_count() + ctas / 2) / ctas;
     S = S < 1 ? 1 : (S > 8 ? 8 : S);

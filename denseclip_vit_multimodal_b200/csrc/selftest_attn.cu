@@ -156,6 +156,37 @@ int main(int argc, char** argv) {
     }
     return 0;
   }
+  if (argc > 4 && !strcmp(argv[1], "timeline4")) {  // P4 kernel: per-warpgroup sub-tile stamps of one CTA
+    const int B = atoi(argv[2]), H = atoi(argv[3]), N = atoi(argv[4]);
+    const int D = H * 64, ld = 3 * D;
+    __nv_bfloat16 *qkv, *out;
+    long long* dbg;
+    cudaMalloc(&qkv, size_t(B) * N * ld * 2); cudaMalloc(&out, size_t(B) * N * D * 2); cudaMalloc(&dbg, 2048 * 8);
+    fill_bf16<<<(size_t(B) * N * ld + 255) / 256, 256>>>(qkv, size_t(B) * N * ld, 11u, 2.0f);
+    AttnOperands op{qkv, qkv, qkv, ld, ld, ld, (long long)N * ld, (long long)N * ld, (long long)N * ld, N};
+    AttnParams p{};
+    p.B = B; p.H = H; p.Nq_total = N; p.q_start = 0; p.Nk = N; p.q_col0 = 0; p.k_col0 = D; p.v_col0 = 2 * D;
+    p.scale_log2 = 0.125f * 1.4426950408889634f; p.out = out; p.out_batch_stride = (long long)N * D; p.ldo = D;
+    cudaMemset(dbg, 0, 2048 * 8);
+    p.dbg = dbg; p.dbg_cta = getenv("DCLIP_TL_CTA") ? atoi(getenv("DCLIP_TL_CTA")) : 70;
+    AttnPlan plan = make_attn_plan(op, p);
+    run_attn(plan, 0);
+    cudaDeviceSynchronize();
+    std::vector<long long> h(2048);
+    cudaMemcpy(h.data(), dbg, 2048 * 8, cudaMemcpyDeviceToHost);
+    long long t0 = h[0];
+    for (int w = 1; w < 4; ++w) if (h[w * 40 * 8] && h[w * 40 * 8] < t0) t0 = h[w * 40 * 8];
+    printf("P4 timeline CTA %d (cycles rel. to first wait)  cols: wait_start s_full_got softmax_done wg_barrier_done pv_issued next_qk_issued\n", p.dbg_cta);
+    const int nrows = getenv("DCLIP_TL_ROWS") ? atoi(getenv("DCLIP_TL_ROWS")) : 36;
+    for (int c = 0; c < nrows; ++c)
+      for (int w = 0; w < 4; ++w) {
+        const long long* d = &h[(w * 40 + c) * 8];
+        printf("wg%d c=%2d  %7lld %7lld %7lld %7lld %7lld %7lld   (wait %5lld softmax %5lld barrier %4lld pv_issue %4lld qk_issue %4lld | qk->s_full %5lld)\n", w, c, d[0] - t0, d[1] - t0,
+               d[2] - t0, d[3] - t0, d[4] - t0, d[5] - t0, d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[5] - d[4],
+               (c + 1 < 40 && d[8 + 1] && d[5]) ? d[8 + 1] - d[5] : 0);
+      }
+    return 0;
+  }
   if (argc > 5 && !strcmp(argv[1], "qstart")) {  // time the launch restricted to query rows >= q_start (no check)
     const int B = atoi(argv[2]), H = atoi(argv[3]), N = atoi(argv[4]), qs = atoi(argv[5]);
     const int D = H * 64, ld = 3 * D;

@@ -11,6 +11,13 @@ import torch
 import torch.distributed as dist
 
 
+class _NoReduce:
+    """sentinel: statistics are already reduced"""
+
+
+_NO_REDUCE = _NoReduce()
+
+
 def shard_range(n_items: int, world: int, rank: int):
     """Contiguous [start, stop) slice of `n_items` images for `rank`; sizes differ by at most one, order is preserved."""
     if world <= 0 or not 0 <= rank < world:
@@ -64,7 +71,7 @@ def shard_eval_stats(pred: torch.Tensor, target: torch.Tensor, num_classes: int,
 def reduce_eval_stats(conf: torch.Tensor, depth_sq_err_sum: torch.Tensor, depth_count: torch.Tensor, group=None):
     """All-reduce (sum) the evaluation statistics of all shards: 19x19 confusion matrix + depth squared-error sum/count.
     Returns (conf, mIoU, pixel_acc, rmse)."""
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
+    if not isinstance(group, _NoReduce) and dist.is_initialized() and dist.get_world_size(group) > 1:
         for t in (conf, depth_sq_err_sum, depth_count):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     tp = conf.diag().double()
@@ -74,3 +81,21 @@ def reduce_eval_stats(conf: torch.Tensor, depth_sq_err_sum: torch.Tensor, depth_
     acc = float(tp.sum() / conf.sum().clamp(min=1))
     rmse = float(torch.sqrt(depth_sq_err_sum.double() / depth_count.double().clamp(min=1)))
     return conf, miou, acc, rmse
+
+
+def reduce_eval_stats_packed(conf: torch.Tensor, depth_stats: torch.Tensor, group=None) -> torch.Tensor:
+    """ONE collective per step: the int64 [K, K] confusion matrix and the float64 [2] depth (sum sq err, count) travel as a
+    single float64 vector (counts are exact in float64 up to 2^53).  Returns the reduced vector [K*K + 2]; unpack with
+    ``unpack_eval_stats``."""
+    packed = torch.cat([conf.reshape(-1).to(torch.float64), depth_stats.reshape(-1).to(torch.float64)])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed
+
+
+def unpack_eval_stats(packed: torch.Tensor, num_classes: int):
+    """-> (conf int64 [K, K], mIoU, pixel_acc, rmse) from the vector of ``reduce_eval_stats_packed``."""
+    kk = num_classes * num_classes
+    conf = packed[:kk].round().to(torch.int64).reshape(num_classes, num_classes)
+    return reduce_eval_stats(conf, packed[kk].clone(), packed[kk + 1].clone(), group=_NO_REDUCE)
+

@@ -34,6 +34,11 @@ class PipelinedPredictor:
         self.n_submitted = 0
         self.n_collected = 0
         self.has_depth = True
+        # optional consumer of the DEVICE results of a slot (e.g. the multi-GPU gather / eval-statistics reduce of
+        # bench.py): called as post(slot) right after the slot's results are complete on the compute stream (it must
+        # wait on ev_out[slot] on its own stream) and returns an event that the next overwrite of the slot waits for
+        self.post = None
+        self.ev_post = [None] * depth
 
     @torch.no_grad()
     def submit(self, host_batch: torch.Tensor):
@@ -47,6 +52,8 @@ class PipelinedPredictor:
             self.ev_in[s].record(self.copy_stream)
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(self.ev_in[s])
+            if self.ev_post[s] is not None:      # the previous results of this slot are still being consumed on the device
+                self.compute_stream.wait_event(self.ev_post[s])
             out = self.model.predict(self.in_dev[s])
             self.ev_free[s].record(self.compute_stream)
             self.seg_dev[s].copy_(out["seg"], non_blocking=True)       # results may live in CUDA-graph static buffers
@@ -55,6 +62,8 @@ class PipelinedPredictor:
             else:
                 self.has_depth = False
             self.ev_out[s].record(self.compute_stream)
+        if self.post is not None:
+            self.ev_post[s] = self.post(s)
         with torch.cuda.stream(self.out_stream):
             self.out_stream.wait_event(self.ev_out[s])
             self.seg_host[s].copy_(self.seg_dev[s], non_blocking=True)
