@@ -55,7 +55,12 @@ struct GemmParams {
 };
 
 // Compile-time epilogue specialisation. ACT < 0 / FLAGS < 0 select the generic (runtime-checked) epilogue.
-enum GemmEpiFlags : int { EPI_RESID = 1, EPI_OUT_F32 = 2, EPI_OUT_BF16 = 4, EPI_SPLIT = 8, EPI_REMAP = 16, EPI_TMA_STORE = 32 };
+// EPI_CONV_SWAP: grouped implicit 3x3 conv with the operand roles swapped -- the 128 filters of a group are the MMA's M rows
+// (A operand = weights), 256 PIXELS are its N columns (B operand = the TMA-gathered activations), so one tcgen05.mma is
+// 128 x 256 x 16 instead of 128 x 128 x 16: the per-instruction cost of the tensor pipe is the same for N = 128 and 256
+// (profiles/r02_mma_probe.txt), and the 128-filter tile ran at 47% of peak.  The accumulator is then [filter][pixel]; the epilogue
+// writes it transposed (2-byte stores, 64 contiguous bytes per warp instruction) -- negligible next to the K = 6912 mainloop.
+enum GemmEpiFlags : int { EPI_RESID = 1, EPI_OUT_F32 = 2, EPI_OUT_BF16 = 4, EPI_SPLIT = 8, EPI_REMAP = 16, EPI_TMA_STORE = 32, EPI_CONV_SWAP = 64 };
 
 // PAIR: two CTAs of a 2x1x1 cluster form one tcgen05 cta_group::2 unit computing a 256 x BN tile; each CTA stages its
 // own 128 A rows and only HALF of the W tile (BN/2 rows), which cuts the per-SM operand ingest from 48 KB to 32 KB per
@@ -109,7 +114,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  constexpr bool SWAP = FLAGS >= 0 && (FLAGS & EPI_CONV_SWAP) != 0;   // (BN = 256 pixels per tile, BM = 128 filters per group)
+  const int num_m = SWAP ? p.M / BN : (p.M + BM - 1) / BM, num_n = SWAP ? p.conv_G : (p.N + BN - 1) / BN;
   // pair mode: the two CTAs of a pair own m-blocks (2*mp, 2*mp + 1) of the same n-block
   constexpr int cl = PAIR ? 2 : 1;
   const int crank = PAIR ? int(cluster_ctarank()) : 0;
@@ -169,6 +175,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             b_col = (seg == 2 ? p.K : 0) + off;
           }
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          if constexpr (SWAP) {
+            // tile = (256-pixel block m_blk, group n_blk): weights of the group -> A slot (16 KB), pixels -> B slot (32 KB)
+            const int cpb = p.conv_C / BK;
+            const int tap = kb / cpb, c0 = (kb - tap * cpb) * BK;
+            const int img = m_blk / p.conv_tiles_per_img, p0 = (m_blk - img * p.conv_tiles_per_img) * BN;
+            const int y0 = p0 / p.conv_gw, x0 = p0 - y0 * p.conv_gw;
+            tma_load_2d(sa, &tmB, &full_bar[stage], kb * BK, n_blk * BM);
+            tma_load_5d(sa + Cfg::A_BYTES, &tmA, &full_bar[stage], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img, n_blk);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (p.conv_C > 0) {
             const int kc = kb % kseg;                     // k-block inside the (ky, kx, c) K range
             const int cpb = p.conv_C / BK;                // k-blocks per filter tap
@@ -240,6 +257,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int sub = lane >> 3;      // row within a group of 4 rows handled per warp instruction
     const int cq = lane & 7;        // 4-column group within the 32-column chunk
     uint32_t it = 0;
+    if constexpr (SWAP) {
+      // accumulator [filter = TMEM lane][pixel = column]: this thread owns filter q*32 + lane of the group and writes its 256
+      // pixels transposed into out_bf16[pixel][group * 128 + filter] (a warp instruction = 32 consecutive filters = 64 B)
+      for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        const int col = n_blk * BM + q * 32 + lane;
+        const float bias = p.bias ? __ldg(p.bias + col) : 0.f;
+        __nv_bfloat16* obase = p.out_bf16 + size_t(m_blk) * BN * p.ldcb + col;
+        mbar_wait(&tfull_bar[as], aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int chunk = half; chunk < BN / 32; chunk += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + as * BN + chunk * 32 + (uint32_t(q * 32) << 16), r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            obase[size_t(chunk * 32 + e) * p.ldcb] = __float2bfloat16(apply_act_t<ACT>(__uint_as_float(r[e]) + bias, p.act) * p.out_scale);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
+    } else
     if constexpr (FLAGS >= 0 && (FLAGS & EPI_TMA_STORE)) {
       // bf16 output through TMA stores: each warp converts its 32 rows x 64 columns (bias + activation applied in the
       // row-per-lane TMEM layout), writes them as one SWIZZLE_128B smem tile and hands it to the TMA engine, which

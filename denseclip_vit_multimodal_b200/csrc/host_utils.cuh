@@ -157,6 +157,7 @@ struct GemmPlan {
   GemmParams p;
   int bn = 0;
   int grid = 0;
+  bool conv_swap = false;   // grouped 3x3 conv with swapped operand roles (EPI_CONV_SWAP)
 };
 
 template <int BN, int ACT, int FLAGS, bool PAIR = false>
@@ -224,6 +225,12 @@ inline void launch_gemm_bn(const GemmPlan& plan, cudaStream_t stream) {
     trace_generic_gemm(BN, p.act, flags, 1, p);
     return launch_gemm_generic<BN, true>(plan, stream);
   } else {
+  if constexpr (BN == 256) {
+    if (plan.conv_swap) {
+      DCLIP_REQUIRE(p.act == ACT_RELU && flags == EPI_OUT_BF16, "swapped grouped conv: bf16 ReLU epilogue only");
+      return launch_gemm_inst<BN, ACT_RELU, EPI_OUT_BF16 | EPI_CONV_SWAP>(plan, stream);
+    }
+  }
   // CTA-pair (cta_group::2) instantiations exist for the 256-wide tile and the hot ViT-block epilogues
   if constexpr (BN == 256) {
     if (p.cluster == 2) {
@@ -308,6 +315,26 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
   plan.p = p;
   plan.bn = bn;
   const uint64_t kcols = p.split_in ? 2ull * p.K : uint64_t(p.K);
+  // grouped conv, 128 filters per group, bf16 ReLU output, grid tileable by 256 pixels: swapped operand roles (see EPI_CONV_SWAP)
+  if (p.conv_C > 0 && p.conv_G > 1 && bn == 128 && !p.split_in && !p.split_out && p.act == ACT_RELU && p.out_bf16 && !p.out_f32 &&
+      !p.residual && p.remap_P == 0 && p.conv_C % 64 == 0 && (op.conv_gh * p.conv_gw) % 256 == 0 && 256 % p.conv_gw == 0 &&
+      DCLIP_KNOB("DCLIP_GEMM_CONV_SWAP", 1)) {
+    const int gw = p.conv_gw, gh = op.conv_gh;
+    DCLIP_REQUIRE(p.K == 9 * p.conv_C && p.M == op.conv_B * gh * gw && p.N == p.conv_G * 128, "grouped conv: inconsistent shape");
+    plan.conv_swap = true;
+    plan.bn = 256;
+    plan.p.conv_tiles_per_img = gh * gw / 256;
+    plan.p.cluster = 1;
+    uint64_t dims[5] = {uint64_t(p.conv_C), uint64_t(gw), uint64_t(gh), uint64_t(op.conv_B), uint64_t(p.conv_G)};
+    uint64_t str[4] = {uint64_t(op.lda) * 2, uint64_t(op.lda) * 2 * gw, uint64_t(op.a_bs) * 2, uint64_t(op.a_gs) * 2};
+    uint32_t box[5] = {64, uint32_t(gw), uint32_t(256 / gw), 1, 1};
+    plan.tmA = make_tmap_bf16(op.A, 5, dims, str, box);
+    plan.tmB = make_tmap_2d_bf16(op.W, p.N, kcols, op.ldw, 128);
+    memset(&plan.tmC, 0, sizeof(plan.tmC));
+    const int tiles = (p.M / 256) * p.conv_G;
+    plan.grid = tiles < sm_count() ? tiles : sm_count();
+    return plan;
+  }
   if (p.conv_C > 0) {
     const int gw = p.conv_gw, gh = op.conv_gh;
     DCLIP_REQUIRE(p.conv_C % 64 == 0 && p.K == 9 * p.conv_C, "implicit conv: C %% 64 == 0 and K == 9*C required");

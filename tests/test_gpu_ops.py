@@ -357,3 +357,25 @@ def test_two_streams_small_attention_scratch_is_per_stream(ops):
         vv = kv[..., D:].reshape(bb, n, H, 64).transpose(1, 2)
         ref = F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2).reshape(bb, 19, D)
         assert rel_err(o, ref) < 2e-5
+
+
+def test_grouped_conv3x3_production_shape_pair_tiles(ops):
+    """The neck's 12 x (conv3x3 768 -> 128 + folded BN + ReLU) as ONE grouped launch at the BASELINE shape (B = 16, 32 x 64
+    grid): the CTA-pair implicit-GEMM tiles (256 pixels x 128 filters per SM pair, 5-D TMA gather, TMA-store epilogue) are
+    only reached at this size.  Checked against F.conv2d on the same bf16-rounded operands for three of the taps."""
+    from denseclip_vit_multimodal_b200 import models as M
+    G, B, gh, gw, C, N = 12, 16, 32, 64, 768, 128
+    P = gh * gw
+    taps = (_rand(G, B, 1 + P, C, seed=71) * 0.5).bfloat16()                  # token-major, CLS row first (as the encoder writes them)
+    w = _rand(G, N, C, 3, 3, scale=(9 * C) ** -0.5, seed=72)
+    b = _rand(G * N, seed=73)
+    w_all = torch.cat([ops.pack_weight(M.conv3x3_weight_to_gemm(w[g]), False) for g in range(G)], 0).contiguous()
+    cat = torch.empty(B * P, G * N, dtype=torch.bfloat16, device="cuda")
+    a = taps[0, :, 1:, :]
+    a2 = a.as_strided((B * P, C), (a.stride(1), 1), a.storage_offset())
+    ops.gemm(a2, w_all, K=9 * C, bias=b, act="relu", out_bf16=cat, M=B * P, block_n=N,
+             conv=dict(C=C, gw=gw, gh=gh, B=B, a_bs=taps.stride(1), G=G, a_gs=taps.stride(0)))
+    for g in (0, 5, 11):
+        x = taps[g, :, 1:, :].float().reshape(B, gh, gw, C).permute(0, 3, 1, 2)
+        ref = F.relu(F.conv2d(x, w[g].bfloat16().float(), b[g * N:(g + 1) * N], padding=1)).permute(0, 2, 3, 1).reshape(B * P, N)
+        assert rel_err(cat[:, g * N:(g + 1) * N], ref) < 1e-2                 # bf16 output rounding
