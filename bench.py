@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch kernels eagerly instead of replaying a captured graph")
+    ap.add_argument("--sweep", default=None, help="comma-separated per-GPU batch sizes: one JSON line per batch from ONE process group "
+                    "(BASELINE configs[4]: global batch 8-128 at 1/2/4/8 GPUs); without it exactly one line is printed")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,6 +224,22 @@ def main():
     model = model.eval().to(dev)
     if not args.no_cuda_graph:
         model.enable_cuda_graph(True)
+    batches = [int(b) for b in args.sweep.split(",")] if args.sweep else [args.batch]
+    for bi, batch in enumerate(batches):
+        args.batch = batch
+        if not args.no_cuda_graph:
+            model.enable_cuda_graph(True)     # drops the previous batch size's graphs (each holds a full set of activations)
+        torch.cuda.empty_cache()
+        measure(args, model, dev, rank, world, local, spec, last=(bi == len(batches) - 1))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure(args, model, dev, rank, world, local, spec, last=True):
+    import torch.distributed as dist
+    from denseclip_vit_multimodal_b200 import _lib, ops
+    from denseclip_vit_multimodal_b200 import distributed as dd
     B, H, W = args.batch, args.height, args.width
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
     host_imgs = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(2)]
@@ -398,7 +416,7 @@ def main():
                  "sm_mhz": r[4], "power_w": r[5], "thermal_or_hw_slowdown": bool(r[6])} for r in per_rank]
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and last:
         from oracle import denseclip_oracle as O  # checker / CPU baseline leg only
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
@@ -458,10 +476,7 @@ def main():
         }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
