@@ -74,12 +74,13 @@ class GemmArgs(C.Structure):
         ("conv_C", C.c_int), ("conv_gw", C.c_int), ("conv_gh", C.c_int), ("conv_B", C.c_int),
         ("a_bs", C.c_longlong),
         ("conv_G", C.c_int), ("a_gs", C.c_longlong),
+        ("wg_C", C.c_int), ("wg_pitch", C.c_int), ("wg_grouped", C.c_int), ("wg_rows", C.c_int),
     ]
 
 
 class VitConfig(C.Structure):
     _fields_ = [("width", C.c_int), ("layers", C.c_int), ("heads", C.c_int), ("patch_size", C.c_int), ("grid0", C.c_int),
-                ("precise", C.c_int)]
+                ("precise", C.c_int), ("ln_fold", C.c_int)]
 
 
 _PP = C.POINTER(C.c_void_p)
@@ -92,6 +93,7 @@ class VitWeights(C.Structure):
         ("ln1_g", _PP), ("ln1_b", _PP), ("ln2_g", _PP), ("ln2_b", _PP),
         ("in_proj_w", _PP), ("in_proj_b", _PP), ("out_proj_w", _PP), ("out_proj_b", _PP),
         ("fc_w", _PP), ("fc_b", _PP), ("proj_w", _PP), ("proj_b", _PP),
+        ("ln1_c", _PP), ("ln2_c", _PP),
     ]
 
 

@@ -8,6 +8,7 @@
 
 #include "host_utils.cuh"
 #include "rowwise.cuh"
+#include "train_tail.cuh"
 #include "vit_encoder.cuh"
 
 using namespace dclip;
@@ -141,6 +142,7 @@ int dclip_gemm(dclip_handle_t h, const dclip_gemm_args* a, void* stream) {
         p.conv_tiles_per_img = a->conv_gh * a->conv_gw / 128;
         p.conv_G = a->conv_G;
       }
+      p.wg_C = a->wg_C; p.wg_pitch = a->wg_pitch; p.wg_grouped = a->wg_grouped; p.wg_rows = a->wg_rows;
       DCLIP_REQUIRE(p.out_f32 || p.out_bf16, "GEMM needs at least one output");
       if (h->gemm_plans.size() > 4096) h->gemm_plans.clear();
       it = h->gemm_plans.emplace(key, make_gemm_plan(op, p, a->block_n)).first;
@@ -288,21 +290,26 @@ int dclip_token_mean(dclip_handle_t h, const float* x, int B, int row0, int P, l
 int dclip_score_map(dclip_handle_t h, const float* vis, long long ld, long long bs, int row0, const float* text, int B,
                     int K, int C, int P, float eps, float* score, void* stream) {
   return guarded(h, [&] {
-    DCLIP_REQUIRE(C % 32 == 0 && C <= 1024, "score map: C=%d must be a multiple of 32 and <= 1024", C);
+    DCLIP_REQUIRE(C % 128 == 0 && C <= 1024, "score map: C=%d must be a multiple of 128 and <= 1024", C);
+    DCLIP_REQUIRE(ld % 4 == 0 && bs % 4 == 0 && (reinterpret_cast<uintptr_t>(vis) & 15) == 0, "score map: vis rows must be 16B aligned");
     const size_t smem = size_t(K) * C * 4;
     DCLIP_REQUIRE(smem <= 200 * 1024, "score map: K*C too large for shared memory");
     ScoreParams p{vis, ld, bs, row0, text, score, B, K, C, P, eps};
-    dim3 grid(std::min((P + 7) / 8, 128), B);
+    // 32 pixels per block and trip (8 warps x 4 pixels); ~4 blocks per SM over all images, so the per-block
+    // staging of the image's text rows (K*C*4 bytes) is amortised over as many pixels as possible
+    DCLIP_REQUIRE((reinterpret_cast<uintptr_t>(text) & 15) == 0, "score map: text must be 16B aligned");
+    const int per_img = std::max(1, std::min((P + 31) / 32, (4 * sm_count() + B - 1) / B));
+    dim3 grid(per_img, B);
     auto launch = [&](auto kern) {
-      DCLIP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      ensure_dyn_smem(kern, 200 * 1024);
       kern<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
     };
-    switch (C / 32) {
+    switch (C / 128) {
+      case 1: launch(score_map_kernel<1>); break;
+      case 2: launch(score_map_kernel<2>); break;
       case 4: launch(score_map_kernel<4>); break;
+      case 6: launch(score_map_kernel<6>); break;
       case 8: launch(score_map_kernel<8>); break;
-      case 16: launch(score_map_kernel<16>); break;
-      case 24: launch(score_map_kernel<24>); break;
-      case 32: launch(score_map_kernel<32>); break;
       default: throw Error{"score map: C must be one of 128, 256, 512, 768, 1024"};
     }
     check_launch(h);
@@ -394,12 +401,144 @@ int dclip_conv3x3_gather(dclip_handle_t h, const void* in, int in_f32, long long
 // ------------------------------------------------------------------------------------------------------------
 // ViT encoder
 // ------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------
+// training mode of the trainable tail (train_tail.cuh)
+// ---------------------------------------------------------------------------------------------------------
+static int col_reduce_blocks(int M) {
+  int nblk = (M + 63) / 64;
+  return nblk < 1 ? 1 : (nblk > 592 ? 592 : nblk);
+}
+
+size_t dclip_col_reduce_workspace(int M, int N) { return size_t(col_reduce_blocks(M)) * 2 * size_t(N > 0 ? N : 1) * sizeof(double); }
+
+int dclip_col_reduce(dclip_handle_t h, const dclip_col_reduce_args* a, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(a && a->a && a->M > 0 && a->N > 0 && a->out0 && (a->mode == 0 || a->mode == 1), "col_reduce: bad arguments");
+    DCLIP_REQUIRE(a->mode == 1 || a->out1, "col_reduce: mode 0 needs out1 (variance)");
+    DCLIP_REQUIRE(!(a->mode == 1 && a->x) || (a->mean && a->rstd && a->gamma && a->beta), "col_reduce: mode 1 with x needs mean / rstd / gamma / beta");
+    ColReduceParams p{};
+    p.a = a->a; p.lda = a->lda; p.x = a->x; p.ldx = a->ldx;
+    p.mean = a->mean; p.rstd = a->rstd; p.gamma = a->gamma; p.beta = a->beta;
+    p.mask = a->mask; p.ldm = a->ldm; p.mask_scale = a->mask_scale;
+    p.relu = a->relu; p.M = a->M; p.N = a->N; p.mode = a->mode;
+    p.nblk = col_reduce_blocks(a->M);
+    p.rows_per_blk = (a->M + p.nblk - 1) / p.nblk;
+    DCLIP_REQUIRE(a->workspace && a->workspace_bytes >= dclip_col_reduce_workspace(a->M, a->N) &&
+                      (reinterpret_cast<uintptr_t>(a->workspace) & 7) == 0, "col_reduce: workspace too small or misaligned");
+    p.part = static_cast<double*>(a->workspace);
+    p.out0 = a->out0; p.out1 = a->out1; p.out2 = a->out2; p.eps = a->eps;
+    p.run_mean = a->run_mean; p.run_var = a->run_var; p.momentum = a->momentum;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    col_reduce_partial_kernel<<<dim3((a->N + 31) / 32, p.nblk), 256, 0, st>>>(p);
+    col_reduce_final_kernel<<<(a->N + 255) / 256, 256, 0, st>>>(p);
+    check_launch(h, 2);
+  });
+}
+
+int dclip_bn_apply(dclip_handle_t h, const dclip_bn_apply_args* a, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(a && a->M > 0 && a->N > 0 && (a->out_f32 || a->out_bf16) && a->mode >= 0 && a->mode <= 2, "bn_apply: bad arguments");
+    DCLIP_REQUIRE(a->mode != 0 || a->x, "bn_apply: mode 0 needs x");
+    DCLIP_REQUIRE(a->mode == 0 || a->a, "bn_apply: backward modes need the upstream gradient");
+    DCLIP_REQUIRE(a->mode != 1 || (a->x && a->mean && a->rstd && a->gamma && a->beta && a->sum_g && a->sum_gx), "bn_apply: mode 1 needs x, the statistics and both sums");
+    DCLIP_REQUIRE(!a->mean || (a->rstd && a->gamma && a->beta), "bn_apply: BatchNorm needs mean, rstd, gamma and beta");
+    BnApplyParams p{};
+    p.a = a->a; p.lda = a->lda; p.x = a->x; p.ldx = a->ldx;
+    p.mean = a->mean; p.rstd = a->rstd; p.gamma = a->gamma; p.beta = a->beta; p.sum_g = a->sum_g; p.sum_gx = a->sum_gx;
+    p.mask = a->mask; p.ldm = a->ldm; p.mask_scale = a->mask_scale;
+    p.relu = a->relu; p.M = a->M; p.N = a->N; p.mode = a->mode;
+    p.out_f32 = a->out_f32; p.ldo = a->ldo; p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); p.ldb = a->ldb;
+    const long long total = (long long)a->M * a->N;
+    const int grid = int(std::min<long long>((total + 255) / 256, 16LL * sm_count()));
+    bn_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    check_launch(h);
+  });
+}
+
+int dclip_transpose_pad(dclip_handle_t h, const void* in, int in_f32, long long ld, int B, int gh, int gw, int C, int pad,
+                        void* out_bf16, long long ldk, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(in && out_bf16 && B > 0 && gh > 0 && gw > 0 && C > 0 && (pad == 0 || pad == 1), "transpose_pad: bad arguments");
+    const long long K = (long long)B * (gh + pad) * (gw + pad);
+    DCLIP_REQUIRE(ldk >= K && ldk % 8 == 0, "transpose_pad: ldk (%lld) must cover %lld padded pixels and be a multiple of 8", ldk, K);
+    TransposePadParams p{in, in_f32, ld, B, gh, gw, C, pad, static_cast<__nv_bfloat16*>(out_bf16), ldk};
+    transpose_pad_kernel<<<dim3(unsigned((ldk + 31) / 32), unsigned((C + 31) / 32)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    check_launch(h);
+  });
+}
+
+int dclip_upsample_bilinear_bwd(dclip_handle_t h, const float* dout, int B, int K, int H, int W, int gh, int gw, float* dtok,
+                                long long ldc, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(dout && dtok && B > 0 && K > 0 && H > 0 && W > 0 && gh > 0 && gw > 0 && ldc >= K, "upsample_bwd: bad arguments");
+    DCLIP_REQUIRE(size_t(W) * 4 <= 48 * 1024, "upsample_bwd: W = %d too wide for the shared-memory line", W);
+    UpsampleBwdParams p{dout, B, K, H, W, gh, gw, dtok, ldc};
+    upsample_bilinear_bwd_kernel<<<unsigned(B) * K * gh, 256, size_t(W) * 4, static_cast<cudaStream_t>(stream)>>>(p);
+    check_launch(h);
+  });
+}
+
+static constexpr int kLossBlocks = 1184;   // 8 x 148
+size_t dclip_loss_workspace(void) { return size_t(kLossBlocks) * 3 * sizeof(double); }
+
+int dclip_ce_loss(dclip_handle_t h, const float* logits, const long long* target, int B, int K, long long HW, int ignore_index,
+                  void* workspace, float* stats, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(logits && target && workspace && stats && B > 0 && K > 0 && HW > 0, "ce_loss: bad arguments");
+    LossParams p{};
+    p.pred = logits; p.target = target; p.B = B; p.K = K; p.HW = HW; p.ignore_index = ignore_index;
+    p.part = static_cast<double*>(workspace); p.nblk = kLossBlocks; p.stats = stats;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ce_loss_partial_kernel<<<kLossBlocks, 256, 0, st>>>(p);
+    loss_final_kernel<<<1, 256, 0, st>>>(p, 0);
+    check_launch(h, 2);
+  });
+}
+
+int dclip_ce_loss_bwd(dclip_handle_t h, const float* logits, const long long* target, int B, int K, long long HW, int ignore_index,
+                      const float* stats, const float* gout, float* grad, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(logits && target && stats && gout && grad && B > 0 && K > 0 && HW > 0, "ce_loss_bwd: bad arguments");
+    LossParams p{};
+    p.pred = logits; p.target = target; p.B = B; p.K = K; p.HW = HW; p.ignore_index = ignore_index;
+    p.stats = const_cast<float*>(stats); p.gout = gout; p.grad = grad;
+    ce_loss_bwd_kernel<<<kLossBlocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    check_launch(h);
+  });
+}
+
+int dclip_silog_loss(dclip_handle_t h, const float* pred, const float* target, const uint8_t* mask, long long n, float lambd,
+                     float eps, void* workspace, float* stats, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(pred && target && workspace && stats && n > 0, "silog_loss: bad arguments");
+    LossParams p{};
+    p.pred = pred; p.ftarget = target; p.mask = mask; p.B = 1; p.HW = n; p.lambd = lambd; p.eps = eps;
+    p.part = static_cast<double*>(workspace); p.nblk = kLossBlocks; p.stats = stats;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    silog_loss_partial_kernel<<<kLossBlocks, 256, 0, st>>>(p);
+    loss_final_kernel<<<1, 256, 0, st>>>(p, 1);
+    check_launch(h, 2);
+  });
+}
+
+int dclip_silog_loss_bwd(dclip_handle_t h, const float* pred, const float* target, const uint8_t* mask, long long n, float lambd,
+                         float eps, const float* stats, const float* gout, float* grad, void* stream) {
+  return guarded(h, [&] {
+    DCLIP_REQUIRE(pred && target && stats && gout && grad && n > 0, "silog_loss_bwd: bad arguments");
+    LossParams p{};
+    p.pred = pred; p.ftarget = target; p.mask = mask; p.B = 1; p.HW = n; p.lambd = lambd; p.eps = eps;
+    p.stats = const_cast<float*>(stats); p.gout = gout; p.grad = grad;
+    silog_loss_bwd_kernel<<<kLossBlocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    check_launch(h);
+  });
+}
+
 int dclip_vit_create(dclip_handle_t h, const dclip_vit_config* cfg, dclip_vit_t* out) {
   return guarded(h, [&] {
     DCLIP_REQUIRE(cfg && out, "null argument");
     auto v = std::make_unique<dclip_vit_s>();
     v->h = h;
-    v->enc.configure(VitConfig{cfg->width, cfg->layers, cfg->heads, cfg->patch_size, cfg->grid0, cfg->precise});
+    v->enc.configure(VitConfig{cfg->width, cfg->layers, cfg->heads, cfg->patch_size, cfg->grid0, cfg->precise, cfg->ln_fold});
     *out = v.release();
   });
 }
@@ -427,6 +566,8 @@ int dclip_vit_set_weights(dclip_vit_t v, const dclip_vit_weights* w) {
       l.out_proj_w = static_cast<const __nv_bfloat16*>(w->out_proj_w[i]); l.out_proj_b = w->out_proj_b[i];
       l.fc_w = static_cast<const __nv_bfloat16*>(w->fc_w[i]); l.fc_b = w->fc_b[i];
       l.proj_w = static_cast<const __nv_bfloat16*>(w->proj_w[i]); l.proj_b = w->proj_b[i];
+      l.ln1_c = w->ln1_c ? w->ln1_c[i] : nullptr;
+      l.ln2_c = w->ln2_c ? w->ln2_c[i] : nullptr;
     }
     v->enc.invalidate_plans();
   });

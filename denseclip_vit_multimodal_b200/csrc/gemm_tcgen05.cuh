@@ -50,6 +50,24 @@ struct GemmParams {
   int conv_C, conv_gw, conv_tiles_per_img;
   int conv_G;    // > 1: grouped conv -- n-block g reads activation group g (5-D map), N = G * BLOCK_N (the neck's 12 taps in one launch)
   int cluster;   // informational: 2 when launched as CTA pairs (PAIR template), else 1
+  // 3x3-conv weight-gradient mode (wg_C > 0; train_tail.py): C[m, t*wg_C + c] = sum_k A[m, k] * W[c, k + shift(t)], t = 0..8,
+  // shift(t) = (t/3 - 1) * wg_pitch + (t%3 - 1): A = dY^T and W = X^T are [channels][padded pixels] matrices whose pixel index
+  // runs over zero-padded images (one pad column per row, one pad row per image), so a filter tap is a pure shift of the K
+  // coordinate of the W tile (TMA coordinates are signed; out-of-range columns read as zero).  N = 9 * wg_C, wg_C % BLOCK_N == 0.
+  // wg_grouped: m-block g (128 rows of A = the 128 filters of group g) pairs with rows g*wg_C .. of W (the neck's 12 taps).
+  int wg_C, wg_pitch, wg_grouped, wg_rows;
+  // LayerNorm folding (bf16 ViT blocks, vit_encoder.cuh): the residual GEMMs (out-proj / c_proj) publish per-row partial
+  // (sum, sum of squares) of the UPDATED residual stream, one float2 slot per (n-block, epilogue warp half), SLOT-MAJOR
+  // (row_stats_out[slot * stats_ld + row], stats_ld >= M: the consumer's lanes = consecutive rows read 256 contiguous bytes
+  // per slot).  Every slot has exactly one writer and the consumer adds the slots in order, so the statistics are
+  // deterministic.  The GEMM that follows (QKV / c_fc) takes the raw bf16 stream as its A operand and normalises in its epilogue:
+  //   LN(x) W^T + b = rstd * (x (gamma*W)^T) - rstd * mean * rowsum(gamma*W) + (b + W beta)
+  // with W := gamma*W and bias := b + W beta folded on the host, ln_c[n] = rowsum of the (bf16-rounded) folded weight.
+  float2* row_stats_out;        // producer side (ld/st epilogues), or null
+  const float2* row_stats_in;   // consumer side (TMA-store epilogue), or null
+  int stats_ld, stats_n;        // slot stride in rows (>= M) / slots to sum on the consumer side (<= 12)
+  const float* ln_c;            // [N]
+  float ln_inv_d, ln_eps;       // 1 / (LayerNorm width), eps
   long long* dbg;  // selftest only (-DDCLIP_GEMM_TIMELINE): clock64 stamps of CTA 0's epilogue warp 4 and MMA warp
   int dbg_mode;  // selftest only: 1 = epilogue drains TMEM but skips staging and stores; 2 = stage but skip global stores
 };
@@ -199,10 +217,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], a_col, m_blk * BM);
           }
-          if constexpr (PAIR)
+          if constexpr (PAIR) {
             tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], b_col, n_blk * BN + crank * (BN / 2));
-          else
-            tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], b_col, n_blk * BN);
+          } else {
+            int b_row = n_blk * BN;
+            if (p.wg_C > 0) {
+              const int cpb = p.wg_C / BN, t = n_blk / cpb;
+              b_row = (p.wg_grouped ? m_blk * p.wg_C : 0) + (n_blk - t * cpb) * BN;
+              b_col += (t / 3 - 1) * p.wg_pitch + (t % 3 - 1);
+            }
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], b_col, b_row);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -290,6 +315,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int m_blk = (tile / num_n) * cl + crank, n_blk = tile % num_n;
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
         const int row0 = m_blk * BM + q * 32;
+        // folded LayerNorm: this thread's row statistics (summed in slot order: deterministic), before the accumulator wait
+        float ln_rstd = 1.f, ln_nm = 0.f;
+        if (p.row_stats_in) {
+          float s1 = 0.f, s2 = 0.f;
+          if (row0 + lane < p.M) {
+            const float2* sp = p.row_stats_in + row0 + lane;
+            // <= 12 slots (2 per producer n-block).  Unconditional loads (the slot index is clamped, surplus slots get weight 0):
+            // a predicated load per slot made the compiler serialise them behind branches (12 exposed DRAM/L2 latencies per tile)
+            float2 t[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) t[j] = __ldg(sp + size_t(min(j, p.stats_n - 1)) * p.stats_ld);
+#pragma unroll
+            for (int j = 0; j < 12; ++j) { const float wj = j < p.stats_n ? 1.f : 0.f; s1 = fmaf(wj, t[j].x, s1); s2 = fmaf(wj, t[j].y, s2); }
+          }
+          const float mean = s1 * p.ln_inv_d;
+          ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_d - mean * mean, 0.f) + p.ln_eps);
+          ln_nm = -ln_rstd * mean;
+        }
         mbar_wait(&tfull_bar[as], aph);
         tc_fence_after();
 #pragma unroll 1
@@ -299,25 +342,44 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           __syncwarp();
 #pragma unroll
           for (int sc = 0; sc < 2; ++sc) {
+            // per-column epilogue constants of this 32-column chunk (same address in every lane: one L1 wavefront each), all
+            // issued BEFORE the TMEM load so their latencies overlap it and each other (loading them per 8 columns inside the
+            // loop below exposed one L1/L2 latency per load: the epilogue, not the MMA, bounded the tile).  Columns >= N are
+            // clamped to the last valid group: the TMA store clips them.
+            float4 bv[8], cv[8];
+            {
+              const int cN = p.N >= 8 ? p.N - 8 : 0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = min(c0 + sc * 32 + 8 * j, cN);
+                bv[2 * j] = bv[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) {
+                  bv[2 * j] = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                  bv[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+                }
+                cv[2 * j] = cv[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.row_stats_in) {
+                  cv[2 * j] = __ldg(reinterpret_cast<const float4*>(p.ln_c + c));
+                  cv[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(p.ln_c + c + 4));
+                }
+              }
+            }
             uint32_t r[32];
             tmem_ld_32x32b_x32(tmem_base + as * BN + cg * 64 + sc * 32 + (uint32_t(q * 32) << 16), r);
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
-              const int c = c0 + sc * 32 + 8 * j;
-              if (p.bias) {
-                if (c < p.N) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-                  v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-                }
-                if (c + 4 < p.N) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
-                  v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-                }
-              }
+              // v = rstd * acc - rstd * mean * ln_c[c] + bias  (plain GEMM: rstd = 1, the ln_c term is 0)
+              const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1], k0 = cv[2 * j], k1 = cv[2 * j + 1];
+              v[0] = fmaf(ln_rstd, __uint_as_float(r[8 * j + 0]), fmaf(ln_nm, k0.x, b0.x));
+              v[1] = fmaf(ln_rstd, __uint_as_float(r[8 * j + 1]), fmaf(ln_nm, k0.y, b0.y));
+              v[2] = fmaf(ln_rstd, __uint_as_float(r[8 * j + 2]), fmaf(ln_nm, k0.z, b0.z));
+              v[3] = fmaf(ln_rstd, __uint_as_float(r[8 * j + 3]), fmaf(ln_nm, k0.w, b0.w));
+              v[4] = fmaf(ln_rstd, __uint_as_float(r[8 * j + 4]), fmaf(ln_nm, k1.x, b1.x));
+              v[5] = fmaf(ln_rstd, __uint_as_float(r[8 * j + 5]), fmaf(ln_nm, k1.y, b1.y));
+              v[6] = fmaf(ln_rstd, __uint_as_float(r[8 * j + 6]), fmaf(ln_nm, k1.z, b1.z));
+              v[7] = fmaf(ln_rstd, __uint_as_float(r[8 * j + 7]), fmaf(ln_nm, k1.w, b1.w));
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = apply_act_t<ACT>(v[e], p.act) * p.out_scale;
               *reinterpret_cast<uint4*>(stg + lane * 128 + (((sc * 4 + j) ^ (lane & 7)) << 4)) =
@@ -397,6 +459,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       DCLIP_GTL(if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 16) p.dbg[it * 8 + 1] = clock64();)
+      // (row_stats_out) this lane's share of the row sums of its 8 rows, accumulated over all chunks of this warp
+      float st1[8], st2[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { st1[k] = 0.f; st2[k] = 0.f; }
       auto process = [&](int chunk, const float4 (&rres)[8], const float4 b4) {
         const int c = n_blk * BN + chunk * 32 + 4 * cq;
         const bool col_ok = c < p.N;  // N % 4 == 0 is required by the launcher
@@ -420,6 +486,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               v.y = apply_act_t<ACT>(v.y + b4.y, p.act) * p.out_scale + rres[k].y;
               v.z = apply_act_t<ACT>(v.z + b4.z, p.act) * p.out_scale + rres[k].z;
               v.w = apply_act_t<ACT>(v.w + b4.w, p.act) * p.out_scale + rres[k].w;
+              if constexpr (FLAGS >= 0 && (FLAGS & EPI_RESID)) {   // (row_stats_out: only the residual GEMMs publish statistics)
+                st1[k] += (v.x + v.y) + (v.z + v.w);
+                st2[k] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+              }
               if (has_f32) *reinterpret_cast<float4*>(p.out_f32 + orow[k] * p.ldc + c) = v;
               if (has_b16) {
                 const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
@@ -455,6 +525,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (lane == 0) {
         if (PAIR && crank != 0) mbar_arrive_remote(&tempty_bar[as], 0);
         else mbar_arrive(&tempty_bar[as]);
+      }
+      if constexpr (FLAGS >= 0 && (FLAGS & EPI_RESID)) {
+        if (p.row_stats_out) {   // warp-uniform: sum over the 8 column groups (lanes that share `sub`); slot = (n-block, warp half)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              st1[k] += __shfl_xor_sync(0xffffffffu, st1[k], o);
+              st2[k] += __shfl_xor_sync(0xffffffffu, st2[k], o);
+            }
+          }
+          if (cq == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (4 * k + sub < rows_valid)
+                p.row_stats_out[size_t(n_blk * 2 + half) * p.stats_ld + orow[k]] = make_float2(st1[k], st2[k]);
+          }
+        }
       }
     }
   }

@@ -22,6 +22,9 @@
 #include "attn_split_tcgen05.cuh"
 #include "attn_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
+#ifdef DCLIP_EXPERIMENTS   // round-2 experiment: column-split softmax (four warpgroups); measured slower (0.424 vs 0.311 ms): profiles/r02_attention_notes.md
+#include "../../scripts/experiments/attn_cs_tcgen05.cuh"
+#endif
 
 namespace dclip {
 
@@ -354,12 +357,18 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
   bool use_cluster = bn == 256 && p.conv_C == 0 && ((num_m_blocks + 1) / 2) * ((p.N + bn - 1) / bn) >= sm_count();
   if (cluster_env == 0) use_cluster = false;
   if (cluster_env == 2 && bn == 256 && p.conv_C == 0) use_cluster = true;
+  if (p.wg_C > 0) {
+    DCLIP_REQUIRE(p.conv_C == 0 && !p.split_in && bn != 192 && p.wg_C % bn == 0 && p.N == 9 * p.wg_C && p.wg_rows >= p.wg_C,
+                  "conv weight-gradient GEMM: N == 9 * wg_C and wg_C %% BLOCK_N == 0 required (wg_C=%d, N=%d, BLOCK_N=%d)", p.wg_C, p.N, bn);
+    if (p.wg_grouped) DCLIP_REQUIRE(p.M % 128 == 0 && p.wg_rows == (p.M / 128) * p.wg_C, "grouped weight-gradient GEMM: 128 filters per group");
+    use_cluster = false;
+  }
   if (bn == 192) {
     DCLIP_REQUIRE(p.conv_C == 0, "BLOCK_N 192: plain GEMM only");
     use_cluster = true;
   }
   plan.p.cluster = use_cluster ? 2 : 1;
-  plan.tmB = make_tmap_2d_bf16(op.W, p.N, kcols, op.ldw, use_cluster ? bn / 2 : bn);
+  plan.tmB = make_tmap_2d_bf16(op.W, p.wg_C > 0 ? p.wg_rows : p.N, kcols, op.ldw, use_cluster ? bn / 2 : bn);
   memset(&plan.tmC, 0, sizeof(plan.tmC));
   const bool no_tma_store = DCLIP_KNOB("DCLIP_GEMM_NO_TMA_STORE", 0) != 0;
   if (!no_tma_store && bn != 192 && p.out_bf16 && !p.out_f32 && !p.residual && !p.split_out && p.remap_P == 0 && p.ldcb % 8 == 0 &&
@@ -371,6 +380,14 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
     plan.tma_store = true;
     plan.tma_store_ptr = p.out_bf16;
   }
+  // LayerNorm folding (GemmParams::row_stats_*): only the epilogues that implement it may be selected
+  if (p.row_stats_in)
+    DCLIP_REQUIRE(plan.tma_store && p.ln_c && p.stats_n >= 1 && p.stats_n <= 12 && p.stats_ld >= p.M && p.N >= 8,
+                  "folded-LayerNorm consumer GEMM needs the TMA-store epilogue (plain bf16 output), ln_c and 1..12 statistics slots");
+  if (p.row_stats_out)
+    DCLIP_REQUIRE(p.residual && p.out_f32 && p.act == ACT_NONE && !p.split_in && !p.split_out && p.remap_P == 0 && p.conv_C == 0 &&
+                      p.stats_ld >= p.M && 2 * ((p.N + bn - 1) / bn) <= 12,
+                  "row statistics are published by the fp32-residual epilogues only (N / BLOCK_N <= 6)");
   const int num_tiles = ((p.M + 127) / 128) * ((p.N + bn - 1) / bn);
   plan.grid = num_tiles < sm_count() ? num_tiles : sm_count();
   if (max_ctas > 0 && plan.grid > max_ctas) plan.grid = max_ctas;
@@ -478,7 +495,7 @@ inline void run_attn_persistent(const AttnPlan& plan, int grid, cudaStream_t str
 // Production dispatch: the persistent kernel (P in TMEM, MUFU token, background tail rows, peeled key 0) whenever there is
 // at least one regular 256-query block; the one-CTA-per-item kernel only serves launches without any (a handful of rows).
 // The variants measured slower in round 1 / 2 (speculative max, deferred P stores, P through shared memory, polynomial exp2,
-// the 4-warpgroup P4 structure) exist only in selftest builds (-DDCLIP_EXPERIMENTS): profiles/r01_attention_notes.md,
+// the 4-warpgroup P4 structure, the column-split CS structure) exist only in selftest builds (-DDCLIP_EXPERIMENTS): profiles/r01_attention_notes.md,
 // profiles/r02_attention_notes.md.
 #ifndef DCLIP_EXPERIMENTS
 inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
@@ -490,6 +507,15 @@ inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
   return run_attn_variant<true, 0, 0>(plan, stream);
 }
 #else
+template <int POLY>
+inline void run_attn_cs(const AttnPlan& plan, int grid, cudaStream_t stream) {
+  using Cfg = AttnCsCfg;
+  ensure_dyn_smem(attn_fwd_cs_kernel<POLY>, Cfg::SMEM_BYTES);
+  attn_fwd_cs_kernel<POLY><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(plan.tmQ, plan.tmK, plan.tmV, plan.tmO, plan.p);
+  DCLIP_CHECK_CUDA(cudaGetLastError());
+}
+
+
 // Production variant: P in TMEM (TS MMA) + DCLIP_ATTN_POLY_DEFAULT of every 4 exp2 pairs on the FMA pipe.
 // A/B knobs (selftests only): DCLIP_ATTN_P_SMEM=1 (P through shared memory), DCLIP_ATTN_POLY=0|1|2.
 #ifndef DCLIP_ATTN_POLY_DEFAULT
@@ -526,6 +552,12 @@ inline void run_attn(const AttnPlan& plan, cudaStream_t stream) {
         return run_attn_p4<0>(plan, grid, stream);
       }
 #endif
+      static const int cs = [] { const char* e = getenv("DCLIP_ATTN_CS"); return e ? atoi(e) : 0; }();
+      if (cs && (q.tail_overlap || rows_last > q.tail_rows_max)) {
+        if (poly == 2) return run_attn_cs<2>(plan, grid, stream);
+        if (poly) return run_attn_cs<1>(plan, grid, stream);
+        return run_attn_cs<0>(plan, grid, stream);
+      }
       if (poly) return run_attn_persistent<1>(plan, grid, stream);
       return run_attn_persistent<0>(plan, grid, stream);
     }

@@ -31,6 +31,9 @@ struct LayerNormParams {
   float* out_f32; long long ldo;
   __nv_bfloat16* out_bf16; long long ldb;
   int split; int split_off;
+  // optional (LayerNorm folding of the ViT blocks): per-row (sum, sum of squares) of the OUTPUT in slot 0 of the slot-major
+  // stats_out[slot * stats_ld + row], slots 1 .. stats_n - 1 zeroed (the layout the residual GEMM epilogues fill per 32-column chunk)
+  float2* stats_out = nullptr; int stats_ld = 0; int stats_n = 0;
 };
 
 template <int VEC>  // VEC = D / 128 float4 chunks per lane
@@ -54,6 +57,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p)
     ss += (a * a + b * b) + (c * c + d * d);
   }
   const float rstd = rsqrtf(warp_sum(ss) / float(p.D) + p.eps);
+  float o1 = 0.f, o2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const int c0 = 4 * (lane + 32 * i);
@@ -64,6 +68,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p)
     y.y = (v[i].y - mean) * rstd * g.y + b.y;
     y.z = (v[i].z - mean) * rstd * g.z + b.z;
     y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    o1 += (y.x + y.y) + (y.z + y.w);
+    o2 += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
     if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (long long)row * p.ldo + c0) = y;
     if (p.out_bf16) {
       __nv_bfloat16* ob = p.out_bf16 + (long long)row * p.ldb + c0;
@@ -75,6 +81,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p)
         *reinterpret_cast<uint2*>(ob + p.split_off) = make_uint2(l0, l1);
       }
     }
+  }
+  if (p.stats_out) {
+    o1 = warp_sum(o1);
+    o2 = warp_sum(o2);
+    for (int j = lane; j < p.stats_n; j += 32) p.stats_out[(long long)j * p.stats_ld + row] = j == 0 ? make_float2(o1, o2) : make_float2(0.f, 0.f);
   }
 }
 
@@ -288,34 +299,101 @@ struct ScoreParams {
   float eps;
 };
 
-template <int NC>  // NC = C / 32 channels per lane
+// Sum of 32 per-lane values across the warp, transposed: on return lane L holds the warp total of v[L] in v[0]
+// (31 shuffles for 32 values instead of 5 per value: at step `o` the lanes with bit `o` set keep the upper half).
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// PIX pixels per warp and trip: the K normalised text rows (smem) are read once per PIX pixels (the one-pixel version read
+// 38 KB of smem per pixel and did 19 five-step warp reductions per pixel: 0.89 TB/s; this one is HBM-bound).
+// Lane l holds channels 4 (l + 32 i) .. + 3 of each pixel (128-bit coalesced loads); C % 128 == 0.
+template <int NC4, int PIX = 4>  // NC4 = C / 128 float4 chunks per lane
 __global__ void __launch_bounds__(256) score_map_kernel(const ScoreParams p) {
   extern __shared__ float st[];  // [K][C] normalised text of this image
   const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int k = w; k < p.K; k += 8) {
-    const float* t = p.text + ((long long)b * p.K + k) * p.C;
-    float ss = 0.f;
-    for (int c = lane; c < p.C; c += 32) ss += t[c] * t[c];
-    const float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), p.eps);
-    for (int c = lane; c < p.C; c += 32) st[k * p.C + c] = t[c] * inv;
+  const int C4 = p.C >> 2;
+  float4* st4w = reinterpret_cast<float4*>(st);
+  {
+    // stage the raw text rows with ONE round of coalesced 128-bit loads (all in flight together), then normalise in smem
+    const float4* t4 = reinterpret_cast<const float4*>(p.text + (long long)b * p.K * p.C);
+    for (int i = threadIdx.x; i < p.K * C4; i += 256) st4w[i] = __ldg(t4 + i);
+    __syncthreads();
+    for (int k = w; k < p.K; k += 8) {
+      float ss = 0.f;
+      for (int c = lane; c < C4; c += 32) {
+        const float4 t = st4w[k * C4 + c];
+        ss += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+      }
+      const float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), p.eps);
+      for (int c = lane; c < C4; c += 32) {
+        float4 t = st4w[k * C4 + c];
+        t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
+        st4w[k * C4 + c] = t;
+      }
+    }
   }
   __syncthreads();
-  for (int px = blockIdx.x * 8 + w; px < p.P; px += gridDim.x * 8) {
-    const float* v = p.vis + (long long)b * p.bs + (long long)(p.row0 + px) * p.ld;
-    float vv[NC];
-    float ss = 0.f;
+  const float4* st4 = reinterpret_cast<const float4*>(st);
+  for (int px0 = (blockIdx.x * 8 + w) * PIX; px0 < p.P; px0 += gridDim.x * 8 * PIX) {
+    float4 vv[PIX][NC4];
+    float inv[PIX];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      vv[i] = v[lane + 32 * i];
-      ss += vv[i] * vv[i];
+    for (int q = 0; q < PIX; ++q) {
+      const int px = min(px0 + q, p.P - 1);   // (a ragged last group recomputes the last pixel; its stores are masked)
+      const float4* v = reinterpret_cast<const float4*>(p.vis + (long long)b * p.bs + (long long)(p.row0 + px) * p.ld);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < NC4; ++i) {
+        vv[q][i] = __ldcs(v + lane + 32 * i);
+        ss += (vv[q][i].x * vv[q][i].x + vv[q][i].y * vv[q][i].y) + (vv[q][i].z * vv[q][i].z + vv[q][i].w * vv[q][i].w);
+      }
+      inv[q] = 1.f / fmaxf(sqrtf(warp_sum(ss)), p.eps);
     }
-    const float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), p.eps);
-    for (int k = 0; k < p.K; ++k) {
-      float acc = 0.f;
+    // classes in rounds of 8: 8 x PIX = 32 partial dot products per lane, one transpose-reduce per round
+    for (int k0 = 0; k0 < p.K; k0 += 32 / PIX) {
+      float acc[32];
 #pragma unroll
-      for (int i = 0; i < NC; ++i) acc += vv[i] * st[k * p.C + lane + 32 * i];
-      acc = warp_sum(acc) * inv;
-      if (lane == 0) p.score[((long long)b * p.K + k) * p.P + px] = acc;
+      for (int kk = 0; kk < 32 / PIX; ++kk) {
+        const int k = min(k0 + kk, p.K - 1);
+        // packed fp32x2 FMAs (two lanes per issue slot): the kernel is issue-bound on the 19 x C multiply-adds per pixel
+        uint64_t a01[PIX], a23[PIX];
+#pragma unroll
+        for (int q = 0; q < PIX; ++q) a01[q] = a23[q] = pack_f32x2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NC4; ++i) {
+          const float4 t = st4[k * C4 + lane + 32 * i];
+          const uint64_t t01 = pack_f32x2(t.x, t.y), t23 = pack_f32x2(t.z, t.w);
+#pragma unroll
+          for (int q = 0; q < PIX; ++q) {
+            a01[q] = fma_f32x2(pack_f32x2(vv[q][i].x, vv[q][i].y), t01, a01[q]);
+            a23[q] = fma_f32x2(pack_f32x2(vv[q][i].z, vv[q][i].w), t23, a23[q]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < PIX; ++q) {
+          float s0, s1, s2, s3;
+          unpack_f32x2(a01[q], s0, s1);
+          unpack_f32x2(a23[q], s2, s3);
+          acc[kk * PIX + q] = (s0 + s1) + (s2 + s3);
+        }
+      }
+      const float tot = warp_transpose_reduce32(acc, lane);   // lane = kk * PIX + q
+      const int k = k0 + lane / PIX, q = lane % PIX;
+      float invq = inv[0];
+#pragma unroll
+      for (int qq = 1; qq < PIX; ++qq) invq = (q == qq) ? inv[qq] : invq;
+      if (k < p.K && px0 + q < p.P) p.score[((long long)b * p.K + k) * p.P + px0 + q] = tot * invq;
     }
   }
 }

@@ -19,12 +19,17 @@ namespace dclip {
 
 struct VitConfig {
   int width = 768, layers = 12, heads = 12, patch = 16, grid0 = 14, precise = 0;
+  // bf16 path only: ln_1 / ln_2 are folded into the QKV / c_fc GEMMs (weights arrive pre-multiplied by gamma, biases with
+  // W beta added, ln1_c / ln2_c = row sums of the folded weights); the residual GEMMs publish bf16(x) and per-row statistics.
+  // Removes the 2 x layers stand-alone LayerNorm passes (each re-read the 100 MB fp32 stream the epilogue had just written).
+  int ln_fold = 0;
 };
 
 struct VitLayerWeights {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   const __nv_bfloat16 *in_proj_w, *out_proj_w, *fc_w, *proj_w;
   const float *in_proj_b, *out_proj_b, *fc_b, *proj_b;
+  const float *ln1_c = nullptr, *ln2_c = nullptr;   // ln_fold: [3D] / [4D] row sums of the folded in_proj / c_fc weights
 };
 
 struct VitWeights {
@@ -62,9 +67,11 @@ class VitEncoder {
   int kp() const { return (3 * cfg.patch * cfg.patch + 7) & ~7; }  // im2col row pitch (elements, per hi/lo half)
 
   struct Layout {
-    size_t x, h, qkv, g, pos, lnp, total;
+    size_t x, h, qkv, g, pos, lnp, xb, xb2, st1, st2, total;
     int gh, gw, P, Ntok, M;
   };
+  bool fold() const { return cfg.ln_fold && !cfg.precise; }
+  static constexpr int kStatSlots = 12;   // per-row partial-statistics slots: 2 per producer n-block (N = width: <= 6 n-blocks)
 
   Layout layout(int B, int H, int W) const {
     Layout L{};
@@ -79,6 +86,12 @@ class VitEncoder {
     L.g = off; off += up(g_bytes > patch_bytes ? g_bytes : patch_bytes);
     L.pos = off; off += up(size_t(L.Ntok) * D * 4);
     L.lnp = off; off += up(M * D * 4);
+    if (fold()) {   // bf16 copies of the residual stream (A operands of QKV / c_fc) and the per-row partial statistics
+      L.xb = off; off += up(M * D * 2);
+      L.xb2 = off; off += up(M * D * 2);
+      L.st1 = off; off += up(M * size_t(kStatSlots) * 8);
+      L.st2 = off; off += up(M * size_t(kStatSlots) * 8);
+    }
     L.total = off;
     return L;
   }
@@ -95,7 +108,7 @@ class VitEncoder {
     DCLIP_REQUIRE(ws_bytes >= L.total, "workspace too small: %zu < %zu", ws_bytes, L.total);
     DCLIP_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024B aligned");
     for (const VitTap& t : outs.taps) DCLIP_REQUIRE(t.layer >= 0 && t.layer < cfg.layers, "tap layer %d out of range", t.layer);
-    build_plans(B, H, W, ws, L);
+    build_plans(B, H, W, ws, L, outs);
     int n = 0;
     const int D = cfg.width, s = cfg.precise ? 2 : 1;
     uint8_t* w8 = static_cast<uint8_t*>(ws);
@@ -119,13 +132,19 @@ class VitEncoder {
     cls_row_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(x, weights.class_embedding, pos, B, L.Ntok, D); ++n;
     // ---- ln_pre (in place on the residual stream) ----
     LayerNormParams lp{x, D, weights.ln_pre_g, weights.ln_pre_b, 1e-5f, L.M, D, x, D, nullptr, 0, 0, 0};
+    if (fold()) {   // also the bf16 copy and the row statistics of its output: layer 0's QKV normalises in its epilogue
+      lp.out_bf16 = reinterpret_cast<__nv_bfloat16*>(w8 + L.xb); lp.ldb = D;
+      lp.stats_out = reinterpret_cast<float2*>(w8 + L.st1); lp.stats_ld = L.M; lp.stats_n = 1;
+    }
     launch_layernorm(lp, st); ++n;
 
     size_t tap_i = 0;
     for (int li = 0; li < cfg.layers; ++li) {
       const VitLayerWeights& lw = weights.layers[li];
-      LayerNormParams l1{x, D, lw.ln1_g, lw.ln1_b, 1e-5f, L.M, D, nullptr, 0, hbuf, (long long)D * s, cfg.precise, D};
-      launch_layernorm(l1, st); ++n;
+      if (!fold()) {
+        LayerNormParams l1{x, D, lw.ln1_g, lw.ln1_b, 1e-5f, L.M, D, nullptr, 0, hbuf, (long long)D * s, cfg.precise, D};
+        launch_layernorm(l1, st); ++n;
+      }
       run_gemm(layer_plans_[li].qkv, st); ++n;
       if (cfg.precise) {
         run_attn_split(attn_split_plan_, st); ++n;   // 3-pass hi|lo tensor-core attention, writes hbuf as hi | lo
@@ -134,8 +153,10 @@ class VitEncoder {
         if (attn_plan_.p.q_start == 1) { run_attn_small(cls_attn_, st); ++n; }
       }
       run_gemm(layer_plans_[li].out_proj, st); ++n;
-      LayerNormParams l2{x, D, lw.ln2_g, lw.ln2_b, 1e-5f, L.M, D, nullptr, 0, hbuf, (long long)D * s, cfg.precise, D};
-      launch_layernorm(l2, st); ++n;
+      if (!fold()) {
+        LayerNormParams l2{x, D, lw.ln2_g, lw.ln2_b, 1e-5f, L.M, D, nullptr, 0, hbuf, (long long)D * s, cfg.precise, D};
+        launch_layernorm(l2, st); ++n;
+      }
       run_gemm(layer_plans_[li].fc, st); ++n;
       // ---- feature taps (models.py:568-582) ----
       while (tap_i < outs.taps.size() && outs.taps[tap_i].layer < li) ++tap_i;
@@ -145,7 +166,9 @@ class VitEncoder {
       if (!last && !cfg.precise)
         for (size_t t = tap_i; t < outs.taps.size() && outs.taps[t].layer == li; ++t)
           if (outs.taps[t].tokens_bf16 && !fused_tap) fused_tap = outs.taps[t].tokens_bf16;
-      if (fused_tap) {
+      if (fold()) {   // (the plan already writes bf16(x) to the tap, or to the shared copy, and the row statistics)
+        run_gemm(layer_plans_[li].proj, st); ++n;
+      } else if (fused_tap) {
         GemmPlan pl = layer_plans_[li].proj;
         pl.p.out_bf16 = fused_tap;
         pl.p.ldcb = D;
@@ -193,7 +216,8 @@ class VitEncoder {
   struct PlanKey {
     int B = 0, H = 0, W = 0;
     void* ws = nullptr;
-    bool operator==(const PlanKey& o) const { return B == o.B && H == o.H && W == o.W && ws == o.ws; }
+    std::vector<void*> taps;   // ln_fold: the bf16 token taps are GEMM operands of the next layer (baked into its tensor map)
+    bool operator==(const PlanKey& o) const { return B == o.B && H == o.H && W == o.W && ws == o.ws && taps == o.taps; }
   };
   struct LayerPlans {
     GemmPlan qkv, out_proj, fc, proj;
@@ -205,8 +229,25 @@ class VitEncoder {
   AttnSplitPlan attn_split_plan_;
   SmallAttnParams cls_attn_;
 
-  void build_plans(int B, int H, int W, void* ws, const Layout& L) {
-    const PlanKey key{B, H, W, ws};
+  // slots a residual GEMM publishes per row: one per (n-block, epilogue warp half)
+  static int stat_slots(const GemmPlan& producer) {
+    const int n = 2 * ((producer.p.N + producer.bn - 1) / producer.bn);
+    DCLIP_REQUIRE(n <= kStatSlots, "ln_fold: %d statistics slots per row (max %d)", n, kStatSlots);
+    return n;
+  }
+
+  void build_plans(int B, int H, int W, void* ws, const Layout& L, const VitOutputs& outs) {
+    PlanKey key{B, H, W, ws, {}};
+    // bf16 destination of layer li's updated residual stream: its token tap if one is requested, else the shared copy
+    std::vector<__nv_bfloat16*> xb_dst(cfg.layers, nullptr);
+    if (fold()) {
+      for (int li = 0; li + 1 < cfg.layers; ++li) {
+        xb_dst[li] = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(ws) + L.xb);
+        for (const VitTap& t : outs.taps)
+          if (t.layer == li && t.tokens_bf16) { xb_dst[li] = t.tokens_bf16; break; }
+        key.taps.push_back(xb_dst[li]);
+      }
+    }
     if (key == plan_key_ && int(layer_plans_.size()) == cfg.layers) return;
     const int D = cfg.width, s = cfg.precise ? 2 : 1, M = L.M;
     uint8_t* w8 = static_cast<uint8_t*>(ws);
@@ -228,10 +269,20 @@ class VitEncoder {
     for (int li = 0; li < cfg.layers; ++li) {
       const VitLayerWeights& lw = weights.layers[li];
       LayerPlans& lp = layer_plans_[li];
+      float2* st1 = fold() ? reinterpret_cast<float2*>(w8 + L.st1) : nullptr;
+      float2* st2 = fold() ? reinterpret_cast<float2*>(w8 + L.st2) : nullptr;
+      const __nv_bfloat16* a_qkv = hbuf;
+      const __nv_bfloat16* a_fc = hbuf;
+      if (fold()) {
+        DCLIP_REQUIRE(lw.ln1_c && lw.ln2_c, "ln_fold: folded-weight row sums (ln1_c / ln2_c) not set");
+        a_qkv = li == 0 ? reinterpret_cast<const __nv_bfloat16*>(w8 + L.xb) : xb_dst[li - 1];
+        a_fc = reinterpret_cast<const __nv_bfloat16*>(w8 + L.xb2);
+      }
       {
-        GemmOperands op{hbuf, D * s, lw.in_proj_w, D * s};
+        GemmOperands op{a_qkv, D * s, lw.in_proj_w, D * s};
         GemmParams p{};
         p.M = M; p.N = 3 * D; p.K = D; p.split_in = cfg.precise; p.bias = lw.in_proj_b; p.out_scale = 1.f;
+        if (fold()) { p.row_stats_in = st1; p.stats_ld = M; p.stats_n = li == 0 ? 1 : stat_slots(layer_plans_[li - 1].proj); p.ln_c = lw.ln1_c; p.ln_inv_d = 1.f / D; p.ln_eps = 1e-5f; }
         p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(w8 + L.qkv);
         if (cfg.precise) { p.ldcb = 6 * D; p.split_out = 1; p.split_out_off = 3 * D; }   // [q k v]_hi | [q k v]_lo
         else p.ldcb = 3 * D;
@@ -242,12 +293,17 @@ class VitEncoder {
         GemmParams p{};
         p.M = M; p.N = D; p.K = D; p.split_in = cfg.precise; p.bias = lw.out_proj_b; p.out_scale = 1.f;
         p.residual = x; p.ldr = D; p.out_f32 = x; p.ldc = D;
+        if (fold()) {
+          p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(w8 + L.xb2); p.ldcb = D;
+          p.row_stats_out = st2; p.stats_ld = M;
+        }
         lp.out_proj = make_gemm_plan(op, p);
       }
       {
-        GemmOperands op{hbuf, D * s, lw.fc_w, D * s};
+        GemmOperands op{a_fc, D * s, lw.fc_w, D * s};
         GemmParams p{};
         p.M = M; p.N = 4 * D; p.K = D; p.split_in = cfg.precise; p.bias = lw.fc_b; p.out_scale = 1.f;
+        if (fold()) { p.row_stats_in = st2; p.stats_ld = M; p.stats_n = stat_slots(lp.out_proj); p.ln_c = lw.ln2_c; p.ln_inv_d = 1.f / D; p.ln_eps = 1e-5f; }
         p.act = cfg.precise ? ACT_QUICKGELU_PRECISE : ACT_QUICKGELU;
         p.out_bf16 = gbuf; p.ldcb = 4 * D * s; p.split_out = cfg.precise; p.split_out_off = 4 * D;
         lp.fc = make_gemm_plan(op, p);
@@ -257,6 +313,10 @@ class VitEncoder {
         GemmParams p{};
         p.M = M; p.N = D; p.K = 4 * D; p.split_in = cfg.precise; p.bias = lw.proj_b; p.out_scale = 1.f;
         p.residual = x; p.ldr = D; p.out_f32 = x; p.ldc = D;
+        if (fold() && li + 1 < cfg.layers) {
+          p.out_bf16 = xb_dst[li]; p.ldcb = D;
+          p.row_stats_out = st1; p.stats_ld = M;
+        }
         lp.proj = make_gemm_plan(op, p);
       }
     }

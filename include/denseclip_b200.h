@@ -75,6 +75,13 @@ typedef struct {
    * outputs each; W is [G*block_n, 9*C], output column g*block_n + n.  One launch for the neck's 12 taps. */
   int conv_G;
   long long a_gs;
+  /* weight gradient of a 3x3 / pad-1 conv (wg_C > 0; backward of models.py:717-760 / torchvision FCNHead, the trainable tail
+   * of train_denseclip.py:1040-1044): A = dY^T [M filters, K] and W = X^T [wg_rows channels, K] are channel-major with the
+   * pixel index k running over ZERO-PADDED images (row pitch wg_pitch = gw + 1, one extra zero row per image: see
+   * dclip_transpose_pad); then C[m, t*wg_C + c] = sum_k A[m,k] * W[c, k + (t/3-1)*wg_pitch + (t%3-1)], t = 0..8 = (ky,kx),
+   * i.e. dW in the (ky, kx, c) order of the forward operand.  N = 9*wg_C, wg_C % block_n == 0.  wg_grouped = 1: rows
+   * 128g..128g+127 of A pair with rows g*wg_C.. of W (G independent convs in one launch, wg_rows = G*wg_C). */
+  int wg_C, wg_pitch, wg_grouped, wg_rows;
 } dclip_gemm_args;
 
 int dclip_gemm(dclip_handle_t h, const dclip_gemm_args* a, void* stream);
@@ -145,10 +152,66 @@ int dclip_gamma_residual(dclip_handle_t h, const float* a, const float* gamma, c
 int dclip_conv3x3_gather(dclip_handle_t h, const void* in, int in_f32, long long ld, long long bs, int row0, int B, int hh,
                          int ww, int C, void* out, long long ldo, void* stream);
 
+/* ---- training mode of the trainable tail -------------------------------------------------------
+ * What loss.backward() reaches in the reference's training step (train_denseclip.py:1226-1330; backbone and text tower
+ * frozen, :1040-1044; the heads read the neck output of the original backbone features, denseclip.py:755-812):
+ * ViTFeatureFusionNeck (models.py:717-782) and the two FCNHeads (denseclip.py:305-349) with BatchNorm on BATCH statistics,
+ * the bilinear resize to the ground-truth size (denseclip.py:838, 849) and CE(ignore_index) + SILog (losses.py:21-79).
+ * Matrix products go through dclip_gemm (implicit conv forward / input gradient, wg_* weight gradient); these entry points
+ * are everything around them.  Activations are token-major fp32 [M = B*gh*gw, N]; reductions are deterministic. */
+typedef struct {
+  const float* a; long long lda;      /* mode 0: the matrix to reduce; mode 1: upstream gradient */
+  const float* x; long long ldx;      /* mode 1: pre-BatchNorm activations (NULL: plain column sums of a = a conv bias gradient) */
+  const float *mean, *rstd, *gamma, *beta;             /* mode 1 with x */
+  const uint8_t* mask; long long ldm; float mask_scale; /* mode 1: dropout keep-mask and 1/(1-p), or NULL */
+  int relu, M, N;
+  int mode;      /* 0: nn.BatchNorm2d training statistics: out0 = mean, out1 = biased var, out2 = rstd (optional), running stats updated
+                  * 1: out0 = sum_rows g (dbeta), out1 = sum_rows g * xhat (dgamma, optional), g = a [* mask] [* (BN(x) > 0)] */
+  void* workspace; size_t workspace_bytes;              /* >= dclip_col_reduce_workspace(M, N) */
+  float *out0, *out1, *out2;
+  float eps;
+  float *run_mean, *run_var; float momentum;            /* mode 0, optional (BatchNorm2d.running_mean / running_var, momentum 0.1) */
+} dclip_col_reduce_args;
+size_t dclip_col_reduce_workspace(int M, int N);
+int dclip_col_reduce(dclip_handle_t h, const dclip_col_reduce_args* a, void* stream);
+
+typedef struct {
+  const float* a; long long lda;      /* modes 1, 2: upstream gradient */
+  const float* x; long long ldx;      /* pre-BatchNorm activations */
+  const float *mean, *rstd, *gamma, *beta;              /* NULL mean: no BatchNorm (y = x) */
+  const float *sum_g, *sum_gx;                          /* mode 1: the two dclip_col_reduce(mode 1) outputs */
+  const uint8_t* mask; long long ldm; float mask_scale;
+  int relu, M, N;
+  int mode;      /* 0: y = dropout(relu(gamma*(x-mean)*rstd + beta));  1: BatchNorm(+ReLU, +dropout) input gradient;  2: g only */
+  float* out_f32; long long ldo;
+  void* out_bf16; long long ldb;
+} dclip_bn_apply_args;
+int dclip_bn_apply(dclip_handle_t h, const dclip_bn_apply_args* a, void* stream);
+
+/* token-major [B*gh*gw, C] (fp32 or bf16) -> channel-major bf16 [C][ldk], k = (b*(gh+pad) + y)*(gw+pad) + x, pad cells and the
+ * tail up to ldk zeroed: the operand layout of the weight-gradient GEMMs (dclip_gemm_args.wg_*; pad = 1 for 3x3 convs, 0 for 1x1) */
+int dclip_transpose_pad(dclip_handle_t h, const void* in, int in_f32, long long ld, int B, int gh, int gw, int C, int pad,
+                        void* out_bf16, long long ldk, void* stream);
+/* backward of F.interpolate(bilinear, align_corners=False): dout NCHW fp32 [B,K,H,W] -> dtok token-major fp32 [B*gh*gw, ldc] */
+int dclip_upsample_bilinear_bwd(dclip_handle_t h, const float* dout, int B, int K, int H, int W, int gh, int gw, float* dtok,
+                                long long ldc, void* stream);
+/* losses: stats = float[4] on the device.  CE: {mean loss over counted pixels, count}; SILog: {loss, T, sum d}.
+ * workspace >= dclip_loss_workspace() bytes.  The *_bwd calls read stats and the upstream scalar gradient gout[0] on the device. */
+size_t dclip_loss_workspace(void);
+int dclip_ce_loss(dclip_handle_t h, const float* logits, const long long* target, int B, int K, long long HW, int ignore_index,
+                  void* workspace, float* stats, void* stream);
+int dclip_ce_loss_bwd(dclip_handle_t h, const float* logits, const long long* target, int B, int K, long long HW, int ignore_index,
+                      const float* stats, const float* gout, float* grad, void* stream);
+int dclip_silog_loss(dclip_handle_t h, const float* pred, const float* target, const uint8_t* mask, long long n, float lambd,
+                     float eps, void* workspace, float* stats, void* stream);
+int dclip_silog_loss_bwd(dclip_handle_t h, const float* pred, const float* target, const uint8_t* mask, long long n, float lambd,
+                         float eps, const float* stats, const float* gout, float* grad, void* stream);
+
 /* ---- CLIPVisionTransformer.forward ---------------------------------------------------------------------------- */
 typedef struct {
   int width, layers, heads, patch_size, grid0; /* grid0 = input_resolution / patch_size (stored pos-emb grid) */
   int precise;                                 /* 0: bf16 tensor-core path; 1: fp32-class path (3-pass hi|lo split GEMMs and attention) */
+  int ln_fold;                                 /* bf16 path: ln_1 / ln_2 folded into the QKV / c_fc GEMMs (see dclip_vit_weights) */
 } dclip_vit_config;
 
 /* All weights stay owned by the caller and must outlive the object.  bf16 matrices are [out, in] row-major; in
@@ -165,6 +228,10 @@ typedef struct {
   const void* const* out_proj_w; const float* const* out_proj_b;  /* [D, D], [D]   */
   const void* const* fc_w;       const float* const* fc_b;        /* [4D, D], [4D] */
   const void* const* proj_w;     const float* const* proj_b;      /* [D, 4D], [D]  */
+  /* ln_fold = 1 (models.py:291-293 ln_1 / ln_2 applied algebraically): in_proj_w / fc_w hold bf16(W * gamma) (gamma of ln_1 /
+   * ln_2 along the input dim), in_proj_b / fc_b hold b + W beta, and ln1_c / ln2_c the fp32 row sums of those bf16 folded
+   * weights ([3D] / [4D]); then LN(x) W^T + b = rstd (x Wf^T) - rstd mean c + bf.  ln1_g .. ln2_b are unused in this mode. */
+  const float* const* ln1_c;     const float* const* ln2_c;
 } dclip_vit_weights;
 
 typedef struct {

@@ -70,3 +70,35 @@ def test_patch14_ragged_grid_against_oracle(precision):
     assert out["seg"].shape == (2, 19, 50, 76)
     assert rel_err(out["seg"], ref["seg"]) <= tol and rel_err(out["depth"], ref["depth"]) <= tol
     assert float((model.last_score_map.cpu() - ref["score"]).abs().max()) <= (1e-4 if precision == "fp32" else 2e-2)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 128, 256)])
+def test_layernorm_fold_matches_plain_layernorm_and_oracle(shape):
+    """bf16 ViT blocks: ln_1 / ln_2 folded into the QKV / c_fc GEMMs (weights pre-multiplied by gamma, row statistics published
+    by the residual epilogues; models.py:291-293 applied algebraically) against (a) the same path with stand-alone LayerNorm
+    kernels and (b) the fp32 oracle.  LayerNorm gamma / beta are far from (1, 0) so a wrong fold would show."""
+    import denseclip_vit_multimodal_b200 as D
+    cfg = O.model_config("tiny", 2)["backbone"]
+    cfg = {k: v for k, v in cfg.items() if k != "type"}
+    torch.manual_seed(5)
+    ref_model = D.CLIPVisionTransformer(**copy.deepcopy(cfg), precision="bf16")
+    sd = O.seeded_state_dict({k: tuple(v.shape) for k, v in ref_model.state_dict().items()}, 33)
+    g = torch.Generator().manual_seed(1)
+    for k in sd:
+        if ".ln_1." in k or ".ln_2." in k:
+            sd[k] = (0.5 + torch.rand(sd[k].shape, generator=g)) if k.endswith("weight") else 0.3 * torch.randn(sd[k].shape, generator=g)
+    B, H, W = shape
+    img = O.synthetic_images(B, H, W, seed=4)
+    outs = {}
+    for fold in (False, True):
+        m = D.CLIPVisionTransformer(**copy.deepcopy(cfg), precision="bf16")
+        m.load_state_dict(sd, strict=True)
+        m.ln_fold = fold
+        m = m.eval().cuda()
+        with torch.no_grad():
+            outs[fold] = [f.float().cpu() for f in m(img.cuda())]
+    with torch.no_grad():
+        ref = O.vit_forward({"backbone." + k: v for k, v in sd.items()}, dict(cfg), img)
+    for a, b, r in zip(outs[False], outs[True], ref):
+        assert rel_err(b, a) < 1e-2, rel_err(b, a)       # two bf16 roundings of the same fp32 function
+        assert rel_err(b, r) < 2e-2 and rel_err(a, r) < 2e-2, (rel_err(b, r), rel_err(a, r))

@@ -379,3 +379,15 @@ def test_grouped_conv3x3_production_shape_pair_tiles(ops):
         x = taps[g, :, 1:, :].float().reshape(B, gh, gw, C).permute(0, 3, 1, 2)
         ref = F.relu(F.conv2d(x, w[g].bfloat16().float(), b[g * N:(g + 1) * N], padding=1)).permute(0, 2, 3, 1).reshape(B * P, N)
         assert rel_err(cat[:, g * N:(g + 1) * N], ref) < 1e-2                 # bf16 output rounding
+
+
+@pytest.mark.parametrize("B,P,C,K", [(2, 2048, 512, 19), (1, 2628, 512, 19), (3, 37, 256, 5), (1, 130, 1024, 33), (2, 5, 128, 1)])
+def test_score_map_ragged_pixels_and_classes(ops, B, P, C, K):
+    """F.normalize x2 + einsum('bchw,bkc->bkhw') (denseclip.py:672-675): 4 pixels per warp and classes in rounds of 8, so pixel
+    counts that are not a multiple of 4 / 32 and class counts that are not a multiple of 8 hit the masked paths."""
+    tok = _rand(B, 1 + P, C, seed=81) * 3
+    text = _rand(B, K, C, seed=82)
+    sm = ops.score_map(tok, 1, P, text)
+    ref = torch.einsum("bpc,bkc->bkp", F.normalize(tok[:, 1:], dim=2), F.normalize(text, dim=2))
+    assert sm.shape == (B, K, P)
+    assert float((sm - ref).abs().max()) < 2e-6
