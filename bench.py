@@ -38,8 +38,28 @@ MODELS = {
 RECORDED_PEAKS = {"hbm_gbs": 6541.8, "bf16_tflops": 1674.0, "bf16_tflops_sustained": 1403.8}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the shipped attention kernel at the default workload
 # (ViT-B/16, B = 16), from the ncu --set full capture committed under profiles/ (see ATTN_TRAFFIC_SOURCE); None = not captured
-ATTN_DRAM_TRAFFIC_BYTES = None
-ATTN_TRAFFIC_SOURCE = None
+ATTN_TRAFFIC_SOURCE = "profiles/r02_attn_ncu_in_forward.txt"
+
+
+def _attn_traffic_from_profile():
+    """Parse dram__bytes_read.sum + dram__bytes_write.sum (one launch) out of the committed ncu summary of the shipped kernel."""
+    path = os.path.join(ROOT, ATTN_TRAFFIC_SOURCE)
+    mul = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, seen = 0.0, 0
+    try:
+        for ln in open(path):
+            f = ln.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in mul:
+                tot += float(f[1]) * mul[f[2]]
+                seen += 1
+            if seen == 2:
+                return tot
+    except OSError:
+        pass
+    return None
+
+
+ATTN_DRAM_TRAFFIC_BYTES = _attn_traffic_from_profile()
 
 
 def peaks():

@@ -78,6 +78,29 @@ class GemmArgs(C.Structure):
     ]
 
 
+class ColReduceArgs(C.Structure):   # mirrors dclip_col_reduce_args
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_longlong), ("x", C.c_void_p), ("ldx", C.c_longlong),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("mask", C.c_void_p), ("ldm", C.c_longlong), ("mask_scale", C.c_float),
+        ("relu", C.c_int), ("M", C.c_int), ("N", C.c_int), ("mode", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("out0", C.c_void_p), ("out1", C.c_void_p), ("out2", C.c_void_p), ("eps", C.c_float),
+        ("run_mean", C.c_void_p), ("run_var", C.c_void_p), ("momentum", C.c_float),
+    ]
+
+
+class BnApplyArgs(C.Structure):   # mirrors dclip_bn_apply_args
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_longlong), ("x", C.c_void_p), ("ldx", C.c_longlong),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("sum_g", C.c_void_p), ("sum_gx", C.c_void_p),
+        ("mask", C.c_void_p), ("ldm", C.c_longlong), ("mask_scale", C.c_float),
+        ("relu", C.c_int), ("M", C.c_int), ("N", C.c_int), ("mode", C.c_int),
+        ("out_f32", C.c_void_p), ("ldo", C.c_longlong), ("out_bf16", C.c_void_p), ("ldb", C.c_longlong),
+    ]
+
+
 class VitConfig(C.Structure):
     _fields_ = [("width", C.c_int), ("layers", C.c_int), ("heads", C.c_int), ("patch_size", C.c_int), ("grid0", C.c_int),
                 ("precise", C.c_int), ("ln_fold", C.c_int)]
@@ -108,6 +131,8 @@ EXPORTS = [
     "dclip_attention_split",
     "dclip_attention_small", "dclip_im2col_patches", "dclip_posemb_interp", "dclip_tap_nchw", "dclip_nchw_to_tokens",
     "dclip_token_mean", "dclip_score_map", "dclip_upsample_bilinear", "dclip_upsample_argmax", "dclip_eval_stats", "dclip_gamma_residual", "dclip_conv3x3_gather",
+    "dclip_col_reduce_workspace", "dclip_col_reduce", "dclip_bn_apply", "dclip_transpose_pad", "dclip_upsample_bilinear_bwd",
+    "dclip_loss_workspace", "dclip_ce_loss", "dclip_ce_loss_bwd", "dclip_silog_loss", "dclip_silog_loss_bwd",
     "dclip_vit_create", "dclip_vit_destroy", "dclip_vit_set_weights", "dclip_vit_workspace_bytes", "dclip_vit_forward",
 ]
 
@@ -145,6 +170,16 @@ def _declare(lib):
     lib.dclip_eval_stats.argtypes = [vp, vp, vp, i, ll, i, i, vp, vp, vp, ll, vp, vp, vp]
     lib.dclip_gamma_residual.argtypes = [vp, vp, vp, vp, vp, ll, i, vp]
     lib.dclip_conv3x3_gather.argtypes = [vp, vp, i, ll, ll, i, i, i, i, i, vp, ll, vp]
+    lib.dclip_col_reduce_workspace.argtypes = [i, i]
+    lib.dclip_col_reduce.argtypes = [vp, C.POINTER(ColReduceArgs), vp]
+    lib.dclip_bn_apply.argtypes = [vp, C.POINTER(BnApplyArgs), vp]
+    lib.dclip_transpose_pad.argtypes = [vp, vp, i, ll, ll, i, i, i, i, i, i, i, i, vp, ll, vp]
+    lib.dclip_upsample_bilinear_bwd.argtypes = [vp, vp, i, i, i, i, i, i, vp, ll, vp]
+    lib.dclip_loss_workspace.argtypes = []
+    lib.dclip_ce_loss.argtypes = [vp, vp, vp, i, i, ll, i, vp, vp, vp]
+    lib.dclip_ce_loss_bwd.argtypes = [vp, vp, vp, i, i, ll, i, vp, vp, vp, vp]
+    lib.dclip_silog_loss.argtypes = [vp, vp, vp, vp, ll, f, f, vp, vp, vp]
+    lib.dclip_silog_loss_bwd.argtypes = [vp, vp, vp, vp, ll, f, f, vp, vp, vp, vp]
     lib.dclip_vit_create.argtypes = [vp, C.POINTER(VitConfig), C.POINTER(vp)]
     lib.dclip_vit_destroy.argtypes = [vp]
     lib.dclip_vit_set_weights.argtypes = [vp, C.POINTER(VitWeights)]
@@ -152,9 +187,12 @@ def _declare(lib):
     lib.dclip_vit_forward.argtypes = [vp, vp, i, i, i, vp, C.c_size_t, C.POINTER(VitOutputs), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("dclip_last_error", "dclip_launch_count", "dclip_sizeof_gemm_args"):
+        if name not in ("dclip_last_error", "dclip_launch_count", "dclip_sizeof_gemm_args", "dclip_col_reduce_workspace",
+                        "dclip_loss_workspace"):
             fn.restype = i
     lib.dclip_sizeof_gemm_args.restype = C.c_size_t
+    lib.dclip_col_reduce_workspace.restype = C.c_size_t
+    lib.dclip_loss_workspace.restype = C.c_size_t
 
 
 def lib():

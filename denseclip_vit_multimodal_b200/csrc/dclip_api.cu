@@ -455,13 +455,14 @@ int dclip_bn_apply(dclip_handle_t h, const dclip_bn_apply_args* a, void* stream)
   });
 }
 
-int dclip_transpose_pad(dclip_handle_t h, const void* in, int in_f32, long long ld, int B, int gh, int gw, int C, int pad,
-                        void* out_bf16, long long ldk, void* stream) {
+int dclip_transpose_pad(dclip_handle_t h, const void* in, int in_f32, long long ld, long long bs, int B, int gh, int gw, int C, int pad,
+                        int pitch, int lead, int shift, void* out_bf16, long long ldk, void* stream) {
   return guarded(h, [&] {
     DCLIP_REQUIRE(in && out_bf16 && B > 0 && gh > 0 && gw > 0 && C > 0 && (pad == 0 || pad == 1), "transpose_pad: bad arguments");
-    const long long K = (long long)B * (gh + pad) * (gw + pad);
-    DCLIP_REQUIRE(ldk >= K && ldk % 8 == 0, "transpose_pad: ldk (%lld) must cover %lld padded pixels and be a multiple of 8", ldk, K);
-    TransposePadParams p{in, in_f32, ld, B, gh, gw, C, pad, static_cast<__nv_bfloat16*>(out_bf16), ldk};
+    DCLIP_REQUIRE(pitch >= gw + pad && lead >= 0 && shift >= -1 && shift <= 1, "transpose_pad: pitch %d < gw + pad, or bad lead / shift", pitch);
+    const long long K = (long long)B * (gh + pad) * pitch;
+    DCLIP_REQUIRE(ldk >= K + lead && ldk % 8 == 0, "transpose_pad: ldk (%lld) must cover lead + %lld padded pixels and be a multiple of 8", ldk, K);
+    TransposePadParams p{in, in_f32, ld, bs, B, gh, gw, C, pad, pitch, lead, shift, static_cast<__nv_bfloat16*>(out_bf16), ldk};
     transpose_pad_kernel<<<dim3(unsigned((ldk + 31) / 32), unsigned((C + 31) / 32)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     check_launch(h);
   });

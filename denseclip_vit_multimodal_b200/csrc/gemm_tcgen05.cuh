@@ -50,11 +50,12 @@ struct GemmParams {
   int conv_C, conv_gw, conv_tiles_per_img;
   int conv_G;    // > 1: grouped conv -- n-block g reads activation group g (5-D map), N = G * BLOCK_N (the neck's 12 taps in one launch)
   int cluster;   // informational: 2 when launched as CTA pairs (PAIR template), else 1
-  // 3x3-conv weight-gradient mode (wg_C > 0; train_tail.py): C[m, t*wg_C + c] = sum_k A[m, k] * W[c, k + shift(t)], t = 0..8,
-  // shift(t) = (t/3 - 1) * wg_pitch + (t%3 - 1): A = dY^T and W = X^T are [channels][padded pixels] matrices whose pixel index
-  // runs over zero-padded images (one pad column per row, one pad row per image), so a filter tap is a pure shift of the K
-  // coordinate of the W tile (TMA coordinates are signed; out-of-range columns read as zero).  N = 9 * wg_C, wg_C % BLOCK_N == 0.
-  // wg_grouped: m-block g (128 rows of A = the 128 filters of group g) pairs with rows g*wg_C .. of W (the neck's 12 taps).
+  // 3x3-conv weight-gradient mode (wg_C > 0; train_tail.py): C[m, t*wg_C + c] = sum_k A[m, k] * Wcopy[t%3][c, k + (t/3)*wg_pitch],
+  // t = 0..8 = (ky, kx).  A = dY^T [filters][padded pixels]; W = three copies of X^T, [3][wg_rows][wg_pitch + padded pixels + ...]:
+  // copy kx is X^T shifted by kx - 1 pixels behind wg_pitch leading zeros (transpose_pad_kernel), the pixel index runs over
+  // zero-padded images with row pitch wg_pitch (% 8 == 0).  The horizontal tap offset is baked into the copies because a TMA box
+  // must start 16-byte aligned in the innermost dimension; the vertical one is a K-coordinate shift by a multiple of wg_pitch.
+  // N = 9 * wg_C, wg_C % BLOCK_N == 0.  wg_grouped: m-block g (the 128 filters of group g) pairs with rows g*wg_C .. of each copy.
   int wg_C, wg_pitch, wg_grouped, wg_rows;
   // LayerNorm folding (bf16 ViT blocks, vit_encoder.cuh): the residual GEMMs (out-proj / c_proj) publish per-row partial
   // (sum, sum of squares) of the UPDATED residual stream, one float2 slot per (n-block, epilogue warp half), SLOT-MAJOR
@@ -223,8 +224,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             int b_row = n_blk * BN;
             if (p.wg_C > 0) {
               const int cpb = p.wg_C / BN, t = n_blk / cpb;
-              b_row = (p.wg_grouped ? m_blk * p.wg_C : 0) + (n_blk - t * cpb) * BN;
-              b_col += (t / 3 - 1) * p.wg_pitch + (t % 3 - 1);
+              b_row = (t % 3) * p.wg_rows + (p.wg_grouped ? m_blk * p.wg_C : 0) + (n_blk - t * cpb) * BN;
+              b_col += (t / 3) * p.wg_pitch;
             }
             tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], b_col, b_row);
           }

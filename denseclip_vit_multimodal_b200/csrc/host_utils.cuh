@@ -358,8 +358,10 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
   if (cluster_env == 0) use_cluster = false;
   if (cluster_env == 2 && bn == 256 && p.conv_C == 0) use_cluster = true;
   if (p.wg_C > 0) {
-    DCLIP_REQUIRE(p.conv_C == 0 && !p.split_in && bn != 192 && p.wg_C % bn == 0 && p.N == 9 * p.wg_C && p.wg_rows >= p.wg_C,
-                  "conv weight-gradient GEMM: N == 9 * wg_C and wg_C %% BLOCK_N == 0 required (wg_C=%d, N=%d, BLOCK_N=%d)", p.wg_C, p.N, bn);
+    DCLIP_REQUIRE(p.conv_C == 0 && !p.split_in && bn != 192 && p.wg_C % bn == 0 && p.N == 9 * p.wg_C && p.wg_rows >= p.wg_C &&
+                      p.wg_pitch > 0 && p.wg_pitch % 8 == 0 && op.ldw >= (long long)p.K + 2 * p.wg_pitch,
+                  "conv weight-gradient GEMM: N == 9 * wg_C, wg_C %% BLOCK_N == 0, wg_pitch %% 8 == 0 and ldw >= K + 2 * wg_pitch required "
+                  "(wg_C=%d, N=%d, BLOCK_N=%d, pitch=%d)", p.wg_C, p.N, bn, p.wg_pitch);
     if (p.wg_grouped) DCLIP_REQUIRE(p.M % 128 == 0 && p.wg_rows == (p.M / 128) * p.wg_C, "grouped weight-gradient GEMM: 128 filters per group");
     use_cluster = false;
   }
@@ -368,7 +370,8 @@ inline GemmPlan make_gemm_plan(const GemmOperands& op, const GemmParams& p, int 
     use_cluster = true;
   }
   plan.p.cluster = use_cluster ? 2 : 1;
-  plan.tmB = make_tmap_2d_bf16(op.W, p.wg_C > 0 ? p.wg_rows : p.N, kcols, op.ldw, use_cluster ? bn / 2 : bn);
+  plan.tmB = p.wg_C > 0 ? make_tmap_2d_bf16(op.W, 3ull * p.wg_rows, uint64_t(op.ldw), op.ldw, bn)
+                        : make_tmap_2d_bf16(op.W, p.N, kcols, op.ldw, use_cluster ? bn / 2 : bn);
   memset(&plan.tmC, 0, sizeof(plan.tmC));
   const bool no_tma_store = DCLIP_KNOB("DCLIP_GEMM_NO_TMA_STORE", 0) != 0;
   if (!no_tma_store && bn != 192 && p.out_bf16 && !p.out_f32 && !p.residual && !p.split_out && p.remap_P == 0 && p.ldcb % 8 == 0 &&

@@ -151,34 +151,37 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Operand layout of the weight-gradient GEMMs: token-major [B*gh*gw, C] (fp32 or bf16) -> channel-major bf16 [C][ldk] with
-// the pixel index k = (b * (gh + pad) + y) * (gw + pad) + x; the pad column / pad row (pad = 1) and the tail k >= B*(gh+pad)*(gw+pad)
-// are written as zeros, so a 3x3 filter tap is a pure shift of k (gemm_tcgen05.cuh, wg mode).  pad = 0: plain transpose
-// (weight gradient of a 1x1 conv).  32x32 tiles through shared memory: reads coalesced along C, writes along k.
+// Operand layout of the weight-gradient GEMMs: token-major [B][gh*gw][C] (fp32 or bf16, row pitch ld, image pitch bs) ->
+// channel-major bf16 [C][ldk] over ZERO-PADDED images: pixel (b, y, x) sits at k0 = (b * (gh + pad) + y) * pitch + x with
+// pitch >= gw + pad (pad = 1: at least one zero column per row and one zero row per image; pad = 0 and pitch = gw: a plain
+// transpose, the 1x1-conv case).  The output column is k = k0 + lead - shift, i.e. out[c][k] = padded[c][k - lead + shift]:
+// `shift` in {-1, 0, +1} produces the three horizontally shifted copies of X^T (TMA box starts must be 16-byte aligned in the
+// innermost dimension, so the kx - 1 element shift of a 3x3 tap cannot be a TMA coordinate; the (ky - 1) * pitch row shift can,
+// with pitch % 8 == 0), `lead` zero columns in front keep every coordinate non-negative.  Everything that is not a pixel is
+// written as zero, up to ldk.  32x32 tiles through shared memory: reads coalesced along C, writes along k.
 // ---------------------------------------------------------------------------------------------------------
 struct TransposePadParams {
-  const void* in; int in_f32; long long ld;
-  int B, gh, gw, C, pad;
-  __nv_bfloat16* out; long long ldk;   // ldk >= K rounded up to the tile; columns [0, ldk) of every row are written
+  const void* in; int in_f32; long long ld, bs;   // row pitch / image pitch in elements
+  int B, gh, gw, C, pad, pitch, lead, shift;
+  __nv_bfloat16* out; long long ldk;
 };
 
 __global__ void __launch_bounds__(256) transpose_pad_kernel(const TransposePadParams p) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int ph = p.gh + p.pad, pw = p.gw + p.pad;
+  const int ph = p.gh + p.pad, pw = p.pitch;
   const long long K = (long long)p.B * ph * pw;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const long long k = k0 + ty + 8 * j;
+    const long long k = (long long)k0 + ty + 8 * j - p.lead + p.shift;   // index into the padded layout
     float v = 0.f;
     const int c = c0 + tx;
-    if (k < K && c < p.C) {
+    if (k >= 0 && k < K && c < p.C) {
       const int x = int(k % pw), y = int((k / pw) % ph), b = int(k / ((long long)pw * ph));
       if (x < p.gw && y < p.gh) {
-        const long long row = ((long long)b * p.gh + y) * p.gw + x;
-        v = p.in_f32 ? static_cast<const float*>(p.in)[row * p.ld + c]
-                     : __bfloat162float(static_cast<const __nv_bfloat16*>(p.in)[row * p.ld + c]);
+        const long long off = (long long)b * p.bs + ((long long)y * p.gw + x) * p.ld + c;
+        v = p.in_f32 ? static_cast<const float*>(p.in)[off] : __bfloat162float(static_cast<const __nv_bfloat16*>(p.in)[off]);
       }
     }
     tile[ty + 8 * j][tx] = v;

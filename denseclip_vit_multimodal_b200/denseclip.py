@@ -431,6 +431,14 @@ class DenseCLIP(nn.Module):
         else:
             text, score, _ = self._tail_native(tokens, gh, gw)
         self.last_text_embeddings, self.last_score_map = text, score
+        if self.training:
+            # training mode (train_denseclip.py:1226): BatchNorm on batch statistics, Dropout, and a tape through neck / heads /
+            # resize (the only part loss.backward() reaches: backbone and text tower are frozen, the score-map branch above is
+            # computed and dropped, denseclip.py:755-812) -- train_tail.py
+            out = self._forward_train(enc, tokens, gh, gw, B, img, gt_semantic_seg, return_loss, kwargs)
+            if side is not None:
+                main.wait_event(join)
+            return out
         # 3. neck
         if self.neck is not None:
             if use_tokens:
@@ -457,6 +465,41 @@ class DenseCLIP(nn.Module):
         if side is not None:
             main.wait_event(join)  # the score map / text embeddings are complete when forward() returns, as before
         return {'seg': seg, 'depth': depth}
+
+    def _forward_train(self, enc, tokens, gh, gw, B, img, gt_semantic_seg, return_loss, kwargs):
+        """Training-mode neck / heads / resize with a tape (train_tail.py).  The tail's GEMM precision follows the model's:
+        precision="fp32" -> three-pass split products (the reference trains in fp32), precision="bf16" -> one bf16 pass."""
+        from . import train_tail as T
+        precise = self.precision == "fp32"
+        for hd in (self.decode_head, self.depth_head):
+            if hd is not None and isinstance(hd, IdentityHead):
+                raise NotImplementedError("IdentityHead has no native token-major path")
+        with torch.enable_grad():
+            if self.neck is not None:
+                if not isinstance(self.neck, ViTFeatureFusionNeck):
+                    raise NotImplementedError("training mode supports the ViTFeatureFusionNeck only")
+                if precise:
+                    taps = [ops.nchw_to_tokens(f)[0].view(B * gh * gw, -1) for f in enc["nchw"]]
+                    fused = T.neck_forward_train(self.neck, taps, 0, gh, gw, split=True)
+                else:
+                    fused = T.neck_forward_train(self.neck, enc["tokens_bf16"], 1, gh, gw, split=False)
+            else:
+                fused = tokens[:, 1:].reshape(B * gh * gw, -1).contiguous()
+            if return_loss:
+                gt = gt_semantic_seg if gt_semantic_seg is not None else kwargs.get('gt_depth', kwargs.get('depth_targets', kwargs.get('seg_targets')))
+                out_hw = tuple(gt.shape[-2:]) if gt is not None else (gh, gw)   # denseclip.py:822-836: no GT shape -> unresized
+            else:
+                out_hw = tuple(img.shape[2:])
+            res = []
+            for hd in (self.decode_head if self.with_decode_head else None, self.depth_head if self.with_depth_head else None):
+                if hd is None:
+                    res.append(None)
+                    continue
+                y, n = T.head_forward_train(hd, fused, B, gh, gw, split=precise)
+                res.append(T.upsample_train(y, B, gh, gw, n, out_hw))
+        if return_loss:
+            return {'main_output': res[0], 'depth_output': res[1], 'aux_losses': {}}
+        return {'seg': res[0], 'depth': res[1]}
 
     def _tail_stream(self, device):
         st = getattr(self, "_tail_side_stream", None)

@@ -76,11 +76,12 @@ typedef struct {
   int conv_G;
   long long a_gs;
   /* weight gradient of a 3x3 / pad-1 conv (wg_C > 0; backward of models.py:717-760 / torchvision FCNHead, the trainable tail
-   * of train_denseclip.py:1040-1044): A = dY^T [M filters, K] and W = X^T [wg_rows channels, K] are channel-major with the
-   * pixel index k running over ZERO-PADDED images (row pitch wg_pitch = gw + 1, one extra zero row per image: see
-   * dclip_transpose_pad); then C[m, t*wg_C + c] = sum_k A[m,k] * W[c, k + (t/3-1)*wg_pitch + (t%3-1)], t = 0..8 = (ky,kx),
-   * i.e. dW in the (ky, kx, c) order of the forward operand.  N = 9*wg_C, wg_C % block_n == 0.  wg_grouped = 1: rows
-   * 128g..128g+127 of A pair with rows g*wg_C.. of W (G independent convs in one launch, wg_rows = G*wg_C). */
+   * of train_denseclip.py:1040-1044): A = dY^T [M filters, K] and W = three copies of X^T, [3][wg_rows channels][K + 2*wg_pitch],
+   * channel-major over ZERO-PADDED images (dclip_transpose_pad: row pitch wg_pitch % 8 == 0, one zero row per image; copy kx holds
+   * X^T shifted by kx - 1 pixels, with wg_pitch leading zeros).  Then C[m, t*wg_C + c] = sum_k A[m,k] * Wcopy[t%3][c, k + (t/3)*wg_pitch],
+   * t = 0..8 = (ky,kx): dW in the (ky, kx, c) order of the forward operand, every TMA box start 16-byte aligned.
+   * N = 9*wg_C, wg_C % block_n == 0.  wg_grouped = 1: rows 128g..128g+127 of A pair with rows g*wg_C.. of each copy
+   * (G independent convs in one launch, wg_rows = G*wg_C). */
   int wg_C, wg_pitch, wg_grouped, wg_rows;
 } dclip_gemm_args;
 
@@ -188,10 +189,13 @@ typedef struct {
 } dclip_bn_apply_args;
 int dclip_bn_apply(dclip_handle_t h, const dclip_bn_apply_args* a, void* stream);
 
-/* token-major [B*gh*gw, C] (fp32 or bf16) -> channel-major bf16 [C][ldk], k = (b*(gh+pad) + y)*(gw+pad) + x, pad cells and the
- * tail up to ldk zeroed: the operand layout of the weight-gradient GEMMs (dclip_gemm_args.wg_*; pad = 1 for 3x3 convs, 0 for 1x1) */
-int dclip_transpose_pad(dclip_handle_t h, const void* in, int in_f32, long long ld, int B, int gh, int gw, int C, int pad,
-                        void* out_bf16, long long ldk, void* stream);
+/* token-major [B][gh*gw][C] (fp32 or bf16; row pitch ld, image pitch bs, in elements) -> channel-major bf16 [C][ldk] over
+ * zero-padded images: out[c][k] = padded[c][k - lead + shift], padded index = (b*(gh+pad) + y)*pitch + x, pitch >= gw + pad,
+ * everything that is not a pixel zeroed up to ldk.  The operand layout of the weight-gradient GEMMs (dclip_gemm_args.wg_*):
+ * pad = 1, pitch % 8 == 0, lead = pitch and shift = -1 / 0 / +1 for the three copies of X^T of a 3x3 conv (dY^T: lead = shift = 0);
+ * pad = 0, pitch = gw for a 1x1 conv (a plain transpose). */
+int dclip_transpose_pad(dclip_handle_t h, const void* in, int in_f32, long long ld, long long bs, int B, int gh, int gw, int C, int pad,
+                        int pitch, int lead, int shift, void* out_bf16, long long ldk, void* stream);
 /* backward of F.interpolate(bilinear, align_corners=False): dout NCHW fp32 [B,K,H,W] -> dtok token-major fp32 [B*gh*gw, ldc] */
 int dclip_upsample_bilinear_bwd(dclip_handle_t h, const float* dout, int B, int K, int H, int W, int gh, int gw, float* dtok,
                                 long long ldc, void* stream);

@@ -304,6 +304,85 @@ def denseclip_forward(sd, cfg, img, return_intermediates=False):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# training step of the trainable tail: restated with torch CPU autograd as the differentiator.
+# Pinned by tests/golden/make_golden_train.py (the UNMODIFIED reference in .train(), its own SILogLoss, .backward()).
+# ---------------------------------------------------------------------------------------------------------------
+def conv_bn_relu_train(x, sd, prefix, padding, running):
+    """ConvBNReLU (models.py:13-20) with nn.BatchNorm2d in TRAINING mode: batch statistics, running stats updated with
+    momentum 0.1 (torch default) into ``running`` (a dict of clones, so the caller's state_dict is not touched)."""
+    y = F.conv2d(x, sd[prefix + '.0.weight'], None, padding=padding)
+    rm = running.setdefault(prefix + '.1.running_mean', sd[prefix + '.1.running_mean'].clone())
+    rv = running.setdefault(prefix + '.1.running_var', sd[prefix + '.1.running_var'].clone())
+    y = F.batch_norm(y, rm, rv, sd[prefix + '.1.weight'], sd[prefix + '.1.bias'], True, 0.1, 1e-5)
+    return F.relu(y)
+
+
+def silog_loss(prediction, target, mask=None, lambd=0.5, eps=1e-6):
+    """SILogLoss.forward, losses.py:21-79 (variance form, no square root; 0 when no pixel is valid)."""
+    d = torch.log(torch.clamp(prediction, min=eps)) - torch.log(torch.clamp(target, min=eps))
+    if mask is not None:
+        d = torch.where(mask, d, torch.zeros_like(d))
+        T = int(mask.sum())
+        if T == 0:
+            return prediction.sum() * 0.0
+    else:
+        T = d.numel()
+    return (d ** 2).sum() / T - lambd * (d.sum() ** 2) / (T ** 2)
+
+
+TRAINABLE_PREFIXES = ('neck.', 'decode_head.', 'depth_head.')   # what receives a gradient (see train_forward)
+
+
+def train_forward(sd, cfg, img, out_hw, drop_p=0.0, running=None):
+    """DenseCLIP.forward(return_loss=True) in .train() (denseclip.py:702-891): the heads consume the neck output of the ORIGINAL
+    backbone features (:755-812); outputs are resized to the ground-truth size (:838, :849).  The frozen backbone
+    (train_denseclip.py:1040-1044) runs without a tape.  Dropout(0.1) of the FCNHead is parameterised (drop_p) so a test can
+    switch it off.  Returns (main_output, depth_output, running-stat dict)."""
+    running = {} if running is None else running
+    with torch.no_grad():
+        feats = vit_forward(sd, cfg['backbone'], img)
+    proc = [conv_bn_relu_train(f, sd, f'neck.process_layers.{i}', 1, running) for i, f in enumerate(feats)]
+    x = conv_bn_relu_train(torch.cat(proc, dim=1), sd, 'neck.fusion_layer', 0, running)
+    outs = []
+    for prefix in ('decode_head', 'depth_head'):
+        if not cfg.get(prefix):
+            outs.append(None)
+            continue
+        y = conv_bn_relu_train(x, sd, prefix, 1, running)
+        y = F.dropout(y, drop_p, training=True)
+        y = F.conv2d(y, sd[prefix + '.4.weight'], sd[prefix + '.4.bias'])
+        y = F.conv2d(y, sd[prefix + '.classifier.weight'], sd[prefix + '.classifier.bias'])
+        outs.append(F.interpolate(y, size=out_hw, mode='bilinear', align_corners=False))
+    return outs[0], outs[1], running
+
+
+def train_step(sd, cfg, img, seg_target, depth_target, depth_mask, ignore_index=255, w_seg=1.0, w_silog=0.1, drop_p=0.0):
+    """One loss evaluation + backward of the reference's training step (train_denseclip.py:1226-1330):
+    loss = w_seg * CE(main_output, seg_target, ignore_index) + w_silog * SILog(depth_output, depth_target, depth_mask).
+    Returns dict(main_output, depth_output, loss_seg, loss_silog, loss, grads {key: tensor}, running {key: tensor})."""
+    sdg = {k: (v.clone().requires_grad_(True) if k.startswith(TRAINABLE_PREFIXES) and v.is_floating_point()
+               and 'running_' not in k else v) for k, v in sd.items()}
+    main, depth, running = train_forward(sdg, cfg, img, tuple(seg_target.shape[-2:]), drop_p)
+    loss_seg = F.cross_entropy(main, seg_target, ignore_index=ignore_index)
+    loss_silog = silog_loss(depth, depth_target, depth_mask)
+    loss = w_seg * loss_seg + w_silog * loss_silog
+    loss.backward()
+    grads = {k: v.grad for k, v in sdg.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
+    return dict(main_output=main.detach(), depth_output=depth.detach(), loss_seg=loss_seg.detach(), loss_silog=loss_silog.detach(),
+                loss=loss.detach(), grads=grads, running=running)
+
+
+def synthetic_targets(B, H, W, seed=0, num_classes=19, ignore_index=255):
+    """Deterministic training targets: int64 class map with ~10% ignore pixels, positive depth, boolean validity mask (~80%)."""
+    g = torch.Generator().manual_seed(seed)
+    seg = torch.randint(0, num_classes, (B, H, W), generator=g)
+    seg[torch.rand(B, H, W, generator=g) < 0.1] = ignore_index
+    depth = 0.5 + 20.0 * torch.rand(B, 1, H, W, generator=g)
+    mask = torch.rand(B, 1, H, W, generator=g) < 0.8
+    return seg, depth, mask
+
+
 def synthetic_images(B, H, W, seed=0):
     """CLIP-normalised Cityscapes crops are ~zero-mean/unit-variance per channel."""
     g = torch.Generator().manual_seed(seed)
