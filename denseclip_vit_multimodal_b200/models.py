@@ -268,7 +268,7 @@ class CLIPVisionTransformer(nn.Module):
         _lib.check(h, _lib.lib().dclip_vit_create(h, C.byref(cfg), C.byref(vit)))
         packed = _PackedBlocks(self.transformer, precise, fold_ln=fold)
         keep = dict(
-            conv1=ops.pack_weight(self.conv1.weight, precise, pad_cols_to=8),
+            conv1=ops.pack_weight(self.conv1.weight, precise, pad_cols_to=64 if precise else 8),   # = VitEncoder::kp()
             cls=_f32(self.class_embedding), pos=_f32(self.positional_embedding),
             lpg=_f32(self.ln_pre.weight), lpb=_f32(self.ln_pre.bias), log=_f32(self.ln_post.weight), lob=_f32(self.ln_post.bias),
         )

@@ -54,7 +54,9 @@ typedef struct {
   const void* A;  long long lda;   /* bf16 [M, K] (split_in: [M, 2K] = hi|lo), lda in elements, multiple of 8 */
   const void* W;  long long ldw;   /* bf16 [N, K] (split_in: [N, 2K] = hi|lo) -- torch Linear.weight layout   */
   int M, N, K;                     /* N multiple of 4 */
-  int split_in;                    /* 1: three-pass split-bf16 product (fp32-class accuracy) */
+  int split_in;                    /* 1: three-pass split-bf16 product (fp32-class accuracy).  K % 64 == 0 keeps the halves apart exactly;
+                                    * otherwise the last hi K block also multiplies the first 64 - K % 64 lo columns (an extra lo*lo term,
+                                    * <= 2^-17 relative: below the split's own truncation error) */
   const float* bias;               /* [N] or NULL */
   int act;                         /* DCLIP_ACT_* applied to (acc + bias) */
   float out_scale;                 /* multiplies the activated value (use 1.0f) */
@@ -219,7 +221,8 @@ typedef struct {
 } dclip_vit_config;
 
 /* All weights stay owned by the caller and must outlive the object.  bf16 matrices are [out, in] row-major; in
- * precise mode they are [out, 2*in] = hi|lo halves.  conv1_w is [width, kp] with kp = 3*ps*ps rounded up to 8. */
+ * precise mode they are [out, 2*in] = hi|lo halves.  conv1_w is [width, kp] with kp = 3*ps*ps rounded up to 8
+ * (to 64 in precise mode: each half of a hi|lo operand is a whole number of 64-column K blocks). */
 typedef struct {
   const void* conv1_w;
   const float* class_embedding;       /* [width] */
