@@ -202,6 +202,56 @@ def workload_name(args):
             f"{extra}, 3-layer ContextDecoder + score map{sup}; random init")
 
 
+def time_train_step(model, imgs, iters):
+    """The reference's training step on the drop-in (train_denseclip.py:1040-1044, 1086-1096, 1226-1330): backbone / text encoder
+    frozen, forward in .train() (BatchNorm batch statistics, Dropout), CE(ignore 255) + 0.1 * SILog, backward -- eager, CUDA-event
+    timed, synthetic targets.  Leaves the model in eval mode with its requires_grad flags restored."""
+    from denseclip_vit_multimodal_b200.losses import CrossEntropyLoss, SILogLoss
+    B, _, H, W = imgs.shape
+    g = torch.Generator(device="cpu").manual_seed(3)
+    seg_t = torch.randint(0, 19, (B, H, W), generator=g)
+    seg_t[torch.rand(B, H, W, generator=g) < 0.1] = 255
+    seg_t = seg_t.to(imgs.device)
+    depth_t = (0.5 + 20.0 * torch.rand(B, 1, H, W, generator=g)).to(imgs.device)
+    mask = (torch.rand(B, 1, H, W, generator=g) < 0.8).to(imgs.device)
+    flags = {n: p.requires_grad for n, p in model.named_parameters()}
+    bufs = {n: b.detach().clone() for n, b in model.named_buffers() if "running_" in n or "num_batches" in n}
+    for n, p in model.named_parameters():
+        p.requires_grad = not (n.startswith('backbone.') or n.startswith('text_encoder.'))
+    model.train()
+    ce, sl = CrossEntropyLoss(ignore_index=255), SILogLoss()
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        out = model(imgs, gt_semantic_seg=seg_t, gt_depth=depth_t, return_loss=True)
+        loss = ce(out['main_output'], seg_t) + 0.1 * sl(out['depth_output'], depth_t, mask)
+        loss.backward()
+        return loss
+
+    for _ in range(2):
+        loss = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    n_grads = sum(p.grad is not None for p in model.parameters())
+    model.zero_grad(set_to_none=True)
+    model.eval()
+    for n, p in model.named_parameters():
+        p.requires_grad = flags[n]
+    with torch.no_grad():
+        for n, b in model.named_buffers():
+            if n in bufs:
+                b.copy_(bufs[n])
+    return {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3), "steps": iters, "loss": float(loss.detach()), "parameters_with_grad": n_grads,
+            "what": "forward(.train(), return_loss=True) + CrossEntropyLoss(ignore 255) + 0.1 * SILogLoss + backward of neck / heads / resize; "
+                    "backbone and text encoder frozen; eager launches; GEMM precision follows --precision"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -215,6 +265,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch kernels eagerly instead of replaying a captured graph")
+    ap.add_argument("--train-step", action="store_true", help="also time the TRAINING step of the trainable tail (SURVEY 8(f)-4: forward in "
+                    ".train() + CE(ignore 255) + 0.1 SILog + backward, frozen backbone; train_denseclip.py:1226-1330) and add it as `train_step`")
     ap.add_argument("--sweep", default=None, help="comma-separated per-GPU batch sizes: one JSON line per batch from ONE process group "
                     "(BASELINE configs[4]: global batch 8-128 at 1/2/4/8 GPUs); without it exactly one line is printed")
     args = ap.parse_args()
@@ -460,6 +512,10 @@ def measure(args, model, dev, rank, world, local, spec, last=True):
                         "score_map_max_abs_err_native_vs_port": float((got_score - ref["score"]).abs().max()),
                         "score_map_argmax_agreement_native_vs_port": float((got_score.argmax(1) == ref["score"].argmax(1)).float().mean())}
 
+    train_step = None
+    if args.train_step and rank == 0 and world == 1:
+        train_step = time_train_step(model, dev_imgs[0], max(3, args.steps // 4))
+
     if rank == 0:
         total_imgs_per_s = world * B / (ms_step * 1e-3)
         dtype = "bf16" if args.precision == "bf16" else "bf16x3-split (fp32-class: every product as 3 tensor-core passes over hi|lo operands)"
@@ -496,6 +552,8 @@ def measure(args, model, dev, rank, world, local, spec, last=True):
         }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
+        if train_step:
+            line["train_step"] = train_step
         print(json.dumps(line), flush=True)
 
 

@@ -173,7 +173,7 @@ def _declare(lib):
     lib.dclip_col_reduce_workspace.argtypes = [i, i]
     lib.dclip_col_reduce.argtypes = [vp, C.POINTER(ColReduceArgs), vp]
     lib.dclip_bn_apply.argtypes = [vp, C.POINTER(BnApplyArgs), vp]
-    lib.dclip_transpose_pad.argtypes = [vp, vp, i, ll, ll, i, i, i, i, i, i, i, i, vp, ll, vp]
+    lib.dclip_transpose_pad.argtypes = [vp, vp, i, ll, ll, i, i, i, i, i, i, i, i, i, ll, vp, ll, vp]
     lib.dclip_upsample_bilinear_bwd.argtypes = [vp, vp, i, i, i, i, i, i, vp, ll, vp]
     lib.dclip_loss_workspace.argtypes = []
     lib.dclip_ce_loss.argtypes = [vp, vp, vp, i, i, ll, i, vp, vp, vp]

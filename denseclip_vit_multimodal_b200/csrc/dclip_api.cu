@@ -404,9 +404,9 @@ int dclip_conv3x3_gather(dclip_handle_t h, const void* in, int in_f32, long long
 // ---------------------------------------------------------------------------------------------------------
 // training mode of the trainable tail (train_tail.cuh)
 // ---------------------------------------------------------------------------------------------------------
-static int col_reduce_blocks(int M) {
-  int nblk = (M + 63) / 64;
-  return nblk < 1 ? 1 : (nblk > 592 ? 592 : nblk);
+static int col_reduce_blocks(int M) {   // row blocks of the partial pass: few enough that the finishing pass (one thread per column
+  int nblk = (M + 255) / 256;            // walking the partials) stays in the microseconds, enough to fill the GPU with N / 32 column groups
+  return nblk < 1 ? 1 : (nblk > 64 ? 64 : nblk);
 }
 
 size_t dclip_col_reduce_workspace(int M, int N) { return size_t(col_reduce_blocks(M)) * 2 * size_t(N > 0 ? N : 1) * sizeof(double); }
@@ -456,13 +456,15 @@ int dclip_bn_apply(dclip_handle_t h, const dclip_bn_apply_args* a, void* stream)
 }
 
 int dclip_transpose_pad(dclip_handle_t h, const void* in, int in_f32, long long ld, long long bs, int B, int gh, int gw, int C, int pad,
-                        int pitch, int lead, int shift, void* out_bf16, long long ldk, void* stream) {
+                        int pitch, int lead, int shift, int nshift, long long plane, void* out_bf16, long long ldk, void* stream) {
   return guarded(h, [&] {
     DCLIP_REQUIRE(in && out_bf16 && B > 0 && gh > 0 && gw > 0 && C > 0 && (pad == 0 || pad == 1), "transpose_pad: bad arguments");
     DCLIP_REQUIRE(pitch >= gw + pad && lead >= 0 && shift >= -1 && shift <= 1, "transpose_pad: pitch %d < gw + pad, or bad lead / shift", pitch);
+    DCLIP_REQUIRE(nshift == 1 || (nshift == 3 && plane >= (long long)C * ldk), "transpose_pad: nshift must be 1, or 3 with plane >= C * ldk");
     const long long K = (long long)B * (gh + pad) * pitch;
+    DCLIP_REQUIRE(K < (1ll << 31), "transpose_pad: %lld padded pixels exceed 2^31", K);
     DCLIP_REQUIRE(ldk >= K + lead && ldk % 8 == 0, "transpose_pad: ldk (%lld) must cover lead + %lld padded pixels and be a multiple of 8", ldk, K);
-    TransposePadParams p{in, in_f32, ld, bs, B, gh, gw, C, pad, pitch, lead, shift, static_cast<__nv_bfloat16*>(out_bf16), ldk};
+    TransposePadParams p{in, in_f32, ld, bs, B, gh, gw, C, pad, pitch, lead, shift, static_cast<__nv_bfloat16*>(out_bf16), ldk, nshift, plane};
     transpose_pad_kernel<<<dim3(unsigned((ldk + 31) / 32), unsigned((C + 31) / 32)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     check_launch(h);
   });

@@ -164,34 +164,50 @@ struct TransposePadParams {
   const void* in; int in_f32; long long ld, bs;   // row pitch / image pitch in elements
   int B, gh, gw, C, pad, pitch, lead, shift;
   __nv_bfloat16* out; long long ldk;
+  int nshift; long long plane;   // nshift = 3: planes out + j * plane (j = 0, 1, 2) receive shift = -1, 0, +1 from ONE read of the input
 };
 
+// One block = 32 output columns (k) x 32 channels.  The pixel decode (two integer divisions) is done once per input row of the
+// tile by 34 threads and shared, not per element (the per-element 64-bit divisions made the first version issue-bound at 0.5 TB/s).
 __global__ void __launch_bounds__(256) transpose_pad_kernel(const TransposePadParams p) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[34][33];
+  __shared__ long long src_off[34];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int ph = p.gh + p.pad, pw = p.pitch;
   const long long K = (long long)p.B * ph * pw;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const long long k = (long long)k0 + ty + 8 * j - p.lead + p.shift;   // index into the padded layout
-    float v = 0.f;
-    const int c = c0 + tx;
-    if (k >= 0 && k < K && c < p.C) {
-      const int x = int(k % pw), y = int((k / pw) % ph), b = int(k / ((long long)pw * ph));
-      if (x < p.gw && y < p.gh) {
-        const long long off = (long long)b * p.bs + ((long long)y * p.gw + x) * p.ld + c;
-        v = p.in_f32 ? static_cast<const float*>(p.in)[off] : __bfloat162float(static_cast<const __nv_bfloat16*>(p.in)[off]);
-      }
+  const int lo = p.nshift == 3 ? -1 : p.shift;          // padded index of tile row i: k0 - lead + lo + i
+  const int nrows = p.nshift == 3 ? 34 : 32;
+  if (threadIdx.x < nrows) {
+    const long long k = (long long)k0 - p.lead + lo + threadIdx.x;
+    long long off = -1;
+    if (k >= 0 && k < K) {
+      const unsigned ku = unsigned(k);                   // K < 2^31 (checked by the launcher)
+      const unsigned row = ku / unsigned(pw), x = ku - row * unsigned(pw);
+      const unsigned b = row / unsigned(ph), y = row - b * unsigned(ph);
+      if (int(x) < p.gw && int(y) < p.gh) off = (long long)b * p.bs + ((long long)y * p.gw + x) * p.ld;
     }
-    tile[ty + 8 * j][tx] = v;
+    src_off[threadIdx.x] = off;
   }
   __syncthreads();
+  const int c = c0 + tx;
+  for (int i = ty; i < nrows; i += 8) {
+    const long long off = src_off[i];
+    float v = 0.f;
+    if (off >= 0 && c < p.C)
+      v = p.in_f32 ? static_cast<const float*>(p.in)[off + c] : __bfloat162float(static_cast<const __nv_bfloat16*>(p.in)[off + c]);
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  const long long k = k0 + tx;
+  if (k >= p.ldk) return;
+  for (int j = 0; j < (p.nshift == 3 ? 3 : 1); ++j) {
+    __nv_bfloat16* o = p.out + j * p.plane;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + ty + 8 * j;
-    const long long k = k0 + tx;
-    if (c < p.C && k < p.ldk) p.out[(long long)c * p.ldk + k] = __float2bfloat16(tile[tx][ty + 8 * j]);
+    for (int q = 0; q < 4; ++q) {
+      const int cc = c0 + ty + 8 * q;
+      if (cc < p.C) o[(long long)cc * p.ldk + k] = __float2bfloat16(tile[tx + j][ty + 8 * q]);
+    }
   }
 }
 

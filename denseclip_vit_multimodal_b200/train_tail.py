@@ -99,9 +99,10 @@ def bn_apply(mode: int, M: int, N: int, *, x=None, g=None, mean=None, rstd=None,
 
 
 def transpose_pad(t: torch.Tensor, B: int, gh: int, gw: int, channels: int, pad: int, *, ld=None, bs=None, pitch=None, lead: int = 0,
-                  shift: int = 0, ldk=None, out=None) -> torch.Tensor:
+                  shift: int = 0, ldk=None, out=None, nshift: int = 1, plane: int = 0) -> torch.Tensor:
     """token-major [B][gh*gw][C] (fp32 or bf16; ``t`` points at the first pixel row) -> bf16 [C, ldk] channel-major over
-    zero-padded images: out[c][k] = padded[c][k - lead + shift], padded index (b*(gh+pad) + y)*pitch + x (dclip_transpose_pad)."""
+    zero-padded images: out[c][k] = padded[c][k - lead + shift], padded index (b*(gh+pad) + y)*pitch + x (dclip_transpose_pad).
+    nshift = 3: one pass writes the copies shift = -1, 0, +1 to out, out + plane, out + 2*plane (elements)."""
     pitch = gw + pad if pitch is None else pitch
     K = B * (gh + pad) * pitch
     if ldk is None:
@@ -111,23 +112,33 @@ def transpose_pad(t: torch.Tensor, B: int, gh: int, gw: int, channels: int, pad:
     ld = t.stride(-2) if ld is None else ld
     bs = gh * gw * ld if bs is None else bs
     ops._call(t, _lib.lib().dclip_transpose_pad, C.c_void_p(t.data_ptr()), int(t.dtype == torch.float32), ld, bs, B, gh, gw,
-              channels, pad, pitch, lead, shift, C.c_void_p(out.data_ptr()), ldk, ops._stream(t))
+              channels, pad, pitch, lead, shift, nshift, plane, C.c_void_p(out.data_ptr()), ldk, ops._stream(t))
     return out
 
 
-def conv3x3_wgrad_operands(dy_b: torch.Tensor, x_tokens: torch.Tensor, geo, filters: int, channels: int, *, dy_ld=None, x_ld=None,
-                           x_bs=None):
-    """Operands of the 3x3 weight-gradient GEMM: dyT bf16 [F, K] and the three horizontally shifted copies of X^T, bf16
-    [3, C, K + 2*pitch] (pitch = gw + 1 rounded up to 8 so every TMA box start is 16-byte aligned; see dclip_gemm_args.wg_*)."""
+def _wgrad_geometry(geo):
+    """(pitch, K): row pitch of the padded pixel axis (gw + 1 rounded up to 8: 16-byte aligned TMA box starts) and its length
+    rounded up to the 64-column K block."""
     pitch = (geo.gw + 1 + 7) // 8 * 8
-    K = (geo.B * (geo.gh + 1) * pitch + 63) // 64 * 64
-    dyT = transpose_pad(dy_b, geo.B, geo.gh, geo.gw, filters, 1, ld=dy_ld, pitch=pitch, ldk=K)
+    return pitch, (geo.B * (geo.gh + 1) * pitch + 63) // 64 * 64
+
+
+def conv3x3_wgrad_x_operand(x_tokens: torch.Tensor, geo, channels: int, *, x_ld=None, x_bs=None, out=None):
+    """The three horizontally shifted copies of X^T, bf16 [3, C, K + 2*pitch] (see dclip_gemm_args.wg_*), from ONE pass over x.
+    ``out``: optional [3, Ctot, ldx] buffer slice view whose planes are ``out.stride(0)`` elements apart (grouped launch)."""
+    pitch, K = _wgrad_geometry(geo)
     ldx = K + 2 * pitch
-    xT3 = torch.empty(3, channels, ldx, dtype=torch.bfloat16, device=dy_b.device)
-    for kx in range(3):
-        transpose_pad(x_tokens, geo.B, geo.gh, geo.gw, channels, 1, ld=x_ld, bs=x_bs, pitch=pitch, lead=pitch, shift=kx - 1, ldk=ldx,
-                      out=xT3[kx])
-    return dyT, xT3, pitch
+    if out is None:
+        out = torch.empty(3, channels, ldx, dtype=torch.bfloat16, device=x_tokens.device)
+    transpose_pad(x_tokens, geo.B, geo.gh, geo.gw, channels, 1, ld=x_ld, bs=x_bs, pitch=pitch, lead=pitch, ldk=ldx, out=out[0],
+                  nshift=3, plane=out.stride(0))
+    return out
+
+
+def conv3x3_wgrad_dy_operand(dy_b: torch.Tensor, geo, filters: int, *, dy_ld=None):
+    """dY^T bf16 [F, K] over the same padded pixel axis."""
+    pitch, K = _wgrad_geometry(geo)
+    return transpose_pad(dy_b, geo.B, geo.gh, geo.gw, filters, 1, ld=dy_ld, pitch=pitch, ldk=K)
 
 
 def upsample_bilinear_bwd(dout: torch.Tensor, gh: int, gw: int, ldc: int) -> torch.Tensor:
@@ -139,14 +150,17 @@ def upsample_bilinear_bwd(dout: torch.Tensor, gh: int, gw: int, ldc: int) -> tor
     return dtok
 
 
-def conv3x3_wgrad(dyT: torch.Tensor, xT3: torch.Tensor, pitch: int, accumulate_into=None) -> torch.Tensor:
-    """dW of a 3x3 / pad-1 conv as ONE GEMM over the padded pixel axis: dyT bf16 [F, K], xT3 bf16 [3, C, K + 2*pitch]
-    (conv3x3_wgrad_operands) -> fp32 [F, 9*C] in the (ky, kx, c) order of the forward operand: output block t = (ky, kx) multiplies
-    dyT with copy kx of X^T read ky*pitch columns further right.  ``accumulate_into``: add to an earlier partial product."""
+def conv3x3_wgrad(dyT: torch.Tensor, xT3: torch.Tensor, pitch: int, accumulate_into=None, groups: int = 1) -> torch.Tensor:
+    """dW of a 3x3 / pad-1 conv as ONE GEMM over the padded pixel axis: dyT bf16 [F, K], xT3 bf16 [3, C, K + 2*pitch] -> fp32
+    [F, 9*C] in the (ky, kx, c) order of the forward operand: output block t = (ky, kx) multiplies dyT with copy kx of X^T read
+    ky*pitch columns further right.  ``groups`` = G > 1: G independent convs in one launch (dyT [G*128, K], xT3 [3, G*C, ...]:
+    filter rows 128g.. pair with channel rows g*C..).  ``accumulate_into``: add to an earlier partial product."""
     F_, K = dyT.shape
-    channels = xT3.shape[1]
+    channels = xT3.shape[1] // groups
     if channels % 64:
         raise DclipError(f"conv3x3 weight gradient: input channels ({channels}) must be a multiple of 64")
+    if groups > 1 and F_ != groups * 128:
+        raise DclipError("grouped conv3x3 weight gradient needs 128 filters per group")
     out = accumulate_into if accumulate_into is not None else torch.empty(F_, 9 * channels, dtype=torch.float32, device=dyT.device)
     g = _lib.GemmArgs()
     g.A, g.lda, g.W, g.ldw = dyT.data_ptr(), dyT.stride(0), xT3.data_ptr(), xT3.stride(1)
@@ -155,7 +169,7 @@ def conv3x3_wgrad(dyT: torch.Tensor, xT3: torch.Tensor, pitch: int, accumulate_i
     g.out_f32, g.ldc = out.data_ptr(), out.stride(0)
     if accumulate_into is not None:
         g.residual, g.ldr = out.data_ptr(), out.stride(0)
-    g.wg_C, g.wg_pitch, g.wg_grouped, g.wg_rows = channels, pitch, 0, channels
+    g.wg_C, g.wg_pitch, g.wg_grouped, g.wg_rows = channels, pitch, int(groups > 1), xT3.shape[1]
     g.block_n = 256 if channels % 256 == 0 else (128 if channels % 128 == 0 else 64)
     ops._call(dyT, _lib.lib().dclip_gemm, C.byref(g), ops._stream(dyT))
     return out
@@ -260,18 +274,12 @@ def _conv_backward(dpre: torch.Tensor, tok_parts, row0: int, geo: _Geom, weight:
     Fp = dy_parts[0].shape[1]
     x_views = [t[:, row0:, :] for t in tok_parts]
     if k == 3:
-        per_dy = [conv3x3_wgrad_operands(d, x_views[0], geo, F_, Cc, dy_ld=d.stride(0), x_ld=tok_parts[0].stride(1),
-                                         x_bs=tok_parts[0].stride(0)) for d in dy_parts[:1]]
-        dyT_hi, xT3_hi, pitch = per_dy[0]
-        dw9 = conv3x3_wgrad(dyT_hi, xT3_hi, pitch)
-        if len(dy_parts) > 1:
-            K = dyT_hi.shape[1]
-            dyT_lo = transpose_pad(dy_parts[1], geo.B, geo.gh, geo.gw, F_, 1, ld=dy_parts[1].stride(0), pitch=pitch, ldk=K)
-            conv3x3_wgrad(dyT_lo, xT3_hi, pitch, accumulate_into=dw9)
-        if len(tok_parts) > 1:
-            _, xT3_lo, _ = conv3x3_wgrad_operands(dy_parts[0], x_views[1], geo, F_, Cc, dy_ld=dy_parts[0].stride(0),
-                                                  x_ld=tok_parts[1].stride(1), x_bs=tok_parts[1].stride(0))
-            conv3x3_wgrad(dyT_hi, xT3_lo, pitch, accumulate_into=dw9)
+        pitch, _ = _wgrad_geometry(geo)
+        dyT = [conv3x3_wgrad_dy_operand(d, geo, F_, dy_ld=d.stride(0)) for d in dy_parts]
+        xT3 = [conv3x3_wgrad_x_operand(v, geo, Cc, x_ld=t.stride(1), x_bs=t.stride(0)) for v, t in zip(x_views, tok_parts)]
+        dw9 = None
+        for a_t, x_t in _pairs(dyT, xT3):
+            dw9 = conv3x3_wgrad(a_t, x_t, pitch, accumulate_into=dw9)
         dw = dw9.view(F_, 3, 3, Cc).permute(0, 3, 1, 2)
     else:
         dyT = [transpose_pad(d, geo.B, geo.gh, geo.gw, F_, 0, ld=d.stride(0)) for d in dy_parts]
@@ -304,6 +312,24 @@ def _tok_parts_of(x: torch.Tensor, geo: _Geom):
 # ---------------------------------------------------------------------------------------------------------------
 # autograd tape
 # ---------------------------------------------------------------------------------------------------------------
+def _grouped_wgrad(dpre: torch.Tensor, flat_parts, nparts: int, row0: int, geo: _Geom, G: int, F_: int, Cc: int) -> torch.Tensor:
+    """Weight gradients of G independent 3x3 convs (128 filters each, same C) in ONE launch per operand pair: dpre fp32 [M, G*F],
+    flat_parts = the taps' operand parts (tap-major).  A per-tap launch is only 9*C/256 = 27 tiles on 148 SMs.  -> fp32 [G*F, 9*C]."""
+    pitch, K = _wgrad_geometry(geo)
+    dyT = [conv3x3_wgrad_dy_operand(d, geo, G * F_, dy_ld=d.stride(0)) for d in _parts(dpre, geo.split)]
+    xT3 = []
+    for part in range(nparts):
+        buf = torch.empty(3, G * Cc, K + 2 * pitch, dtype=torch.bfloat16, device=dpre.device)
+        for i in range(G):
+            t = flat_parts[i * nparts + part]
+            conv3x3_wgrad_x_operand(t[:, row0:, :], geo, Cc, x_ld=t.stride(1), x_bs=t.stride(0), out=buf[:, i * Cc:(i + 1) * Cc])
+        xT3.append(buf)
+    dw_all = None
+    for a_t, x_t in _pairs(dyT, xT3):
+        dw_all = conv3x3_wgrad(a_t, x_t, pitch, accumulate_into=dw_all, groups=G)
+    return dw_all
+
+
 class _ConvBlock(torch.autograd.Function):
     """conv (k = 1 | 3, pad = k // 2) [+ BatchNorm(batch statistics) + ReLU] [+ Dropout] on token-major activations:
     fp32 [M, C] -> fp32 [M, F] (F rounded up to a multiple of 4 with zero columns for a plain 1x1 conv)."""
@@ -400,12 +426,18 @@ class _NeckTaps(torch.autograd.Function):
         sg, sgx = col_grad_sums(gy, pre, mean, rstd, g32, b32, relu=True)
         dpre, _ = bn_apply(1, geo.M, G * F_, x=pre, g=gy, mean=mean, rstd=rstd, gamma=g32, beta=b32, sum_g=sg, sum_gx=sgx, relu=True,
                            want_f32=True)
-        dws, pos = [], 0
-        for i in range(G):
-            parts = flat[pos:pos + ctx.counts[i]]
-            pos += ctx.counts[i]
-            dw, _ = _conv_backward(dpre[:, i * F_:(i + 1) * F_].contiguous(), parts, ctx.row0, geo, ws[i], need_dx=False)
-            dws.append(dw.to(ws[i].dtype))
+        Cc = ws[0].shape[1]
+        same = all(w.shape == ws[0].shape for w in ws) and len(set(ctx.counts)) == 1
+        if same and F_ == 128 and Cc % 64 == 0 and G > 1:
+            dw_all = _grouped_wgrad(dpre, flat, ctx.counts[0], ctx.row0, geo, G, F_, Cc)
+            dws = [dw_all[i * F_:(i + 1) * F_].view(F_, 3, 3, Cc).permute(0, 3, 1, 2).contiguous().to(ws[i].dtype) for i in range(G)]
+        else:
+            dws, pos = [], 0
+            for i in range(G):
+                parts = flat[pos:pos + ctx.counts[i]]
+                pos += ctx.counts[i]
+                dw, _ = _conv_backward(dpre[:, i * F_:(i + 1) * F_].contiguous(), parts, ctx.row0, geo, ws[i], need_dx=False)
+                dws.append(dw.to(ws[i].dtype))
         dg = [sgx[i * F_:(i + 1) * F_] for i in range(G)]
         db = [sg[i * F_:(i + 1) * F_] for i in range(G)]
         return (None, None, None, None, *dws, *dg, *db)

@@ -197,7 +197,8 @@ int dclip_bn_apply(dclip_handle_t h, const dclip_bn_apply_args* a, void* stream)
  * pad = 1, pitch % 8 == 0, lead = pitch and shift = -1 / 0 / +1 for the three copies of X^T of a 3x3 conv (dY^T: lead = shift = 0);
  * pad = 0, pitch = gw for a 1x1 conv (a plain transpose). */
 int dclip_transpose_pad(dclip_handle_t h, const void* in, int in_f32, long long ld, long long bs, int B, int gh, int gw, int C, int pad,
-                        int pitch, int lead, int shift, void* out_bf16, long long ldk, void* stream);
+                        int pitch, int lead, int shift, int nshift, long long plane, void* out_bf16, long long ldk, void* stream);
+/* nshift = 3: ONE read of the input writes the three copies shift = -1, 0, +1 to out_bf16 + j * plane elements (j = 0, 1, 2); `shift` is ignored */
 /* backward of F.interpolate(bilinear, align_corners=False): dout NCHW fp32 [B,K,H,W] -> dtok token-major fp32 [B*gh*gw, ldc] */
 int dclip_upsample_bilinear_bwd(dclip_handle_t h, const float* dout, int B, int K, int H, int W, int gh, int gw, float* dtok,
                                 long long ldc, void* stream);

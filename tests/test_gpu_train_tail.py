@@ -208,3 +208,46 @@ def test_conv3x3_weight_and_input_gradients(B, gh, gw, C, F_, split):
     tol = 2e-5 if split else 1e-4
     assert rel_err(dw, wr.grad) < tol, rel_err(dw, wr.grad)
     assert rel_err(dx, xr.grad.permute(0, 2, 3, 1).reshape(B * gh * gw, C)) < tol
+
+
+def test_conv3x3_weight_gradient_production_shape():
+    """One neck tap at the BASELINE shape (ViT-B/16 @512x1024: 32x64 grid, 768 -> 128 channels, batch 2): the weight-gradient GEMM
+    runs 256-wide tiles over K = 2 * 33 * 72 padded pixels (75 K blocks) with 27 output blocks; bf16 operands vs an fp64 CPU
+    conv2d backward on the same rounded operands."""
+    from denseclip_vit_multimodal_b200 import train_tail as T
+    B, gh, gw, C, F_ = 2, 32, 64, 768, 128
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B * gh * gw, C, generator=g).cuda()
+    dy = torch.randn(B * gh * gw, F_, generator=g).cuda()
+    w = torch.zeros(F_, C, 3, 3).cuda()
+    geo = T._Geom(B, gh, gw, False)
+    dw, _ = T._conv_backward(dy, T._tok_parts_of(x, geo), 0, geo, w, need_dx=False)
+    r = lambda t: t.bfloat16().double().cpu()   # noqa: E731
+    xr = r(x).view(B, gh, gw, C).permute(0, 3, 1, 2).contiguous()
+    gr = r(dy).view(B, gh, gw, F_).permute(0, 3, 1, 2).contiguous()
+    ref = torch.nn.grad.conv2d_weight(xr, (F_, C, 3, 3), gr, padding=1)
+    assert rel_err(dw, ref) < 1e-4, rel_err(dw, ref)
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_grouped_weight_gradient_equals_per_tap(split):
+    """The grouped weight-gradient launch (G convs with 128 filters each in one GEMM per operand pair, the neck's 12 taps) against
+    the per-tap launches and an fp64 CPU reference; taps as bf16 tokens behind a CLS row (row0 = 1), as the encoder delivers them."""
+    from denseclip_vit_multimodal_b200 import train_tail as T
+    G, B, gh, gw, C, F_ = 3, 2, 8, 16, 64, 128
+    g = torch.Generator().manual_seed(8)
+    geo = T._Geom(B, gh, gw, split)
+    xs = [torch.randn(B, gh * gw, C, generator=g) for _ in range(G)]
+    toks = [torch.cat([torch.zeros(B, 1, C), x], 1).cuda().bfloat16().contiguous() for x in xs]
+    dy = torch.randn(B * gh * gw, G * F_, generator=g).cuda()
+    w = torch.zeros(F_, C, 3, 3).cuda()
+    dw_all = T._grouped_wgrad(dy, toks, 1, 1, geo, G, F_, C)
+    r = (lambda t: t.double().cpu()) if split else (lambda t: t.bfloat16().double().cpu())
+    for i in range(G):
+        per_tap, _ = T._conv_backward(dy[:, i * F_:(i + 1) * F_].contiguous(), [toks[i]], 1, geo, w, need_dx=False)
+        got = dw_all[i * F_:(i + 1) * F_].view(F_, 3, 3, C).permute(0, 3, 1, 2)
+        assert rel_err(got, per_tap) < 1e-6
+        xr = toks[i][:, 1:].double().cpu().view(B, gh, gw, C).permute(0, 3, 1, 2).contiguous()
+        gr = r(dy[:, i * F_:(i + 1) * F_]).view(B, gh, gw, F_).permute(0, 3, 1, 2).contiguous()
+        ref = torch.nn.grad.conv2d_weight(xr, (F_, C, 3, 3), gr, padding=1)
+        assert rel_err(got, ref) < (2e-5 if split else 1e-4), (i, rel_err(got, ref))
