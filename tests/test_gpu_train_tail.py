@@ -251,3 +251,36 @@ def test_grouped_weight_gradient_equals_per_tap(split):
         gr = r(dy[:, i * F_:(i + 1) * F_]).view(B, gh, gw, F_).permute(0, 3, 1, 2).contiguous()
         ref = torch.nn.grad.conv2d_weight(xr, (F_, C, 3, 3), gr, padding=1)
         assert rel_err(got, ref) < (2e-5 if split else 1e-4), (i, rel_err(got, ref))
+
+
+def test_training_step_seg_only_config_against_oracle():
+    """A seg-only configuration (no depth head, denseclip.py:343 skipped) in fp32-class precision: main_output and the gradients of
+    every neck / decode-head parameter against torch autograd over the oracle's training forward; depth_output is None."""
+    import denseclip_vit_multimodal_b200 as D
+    from denseclip_vit_multimodal_b200.losses import CrossEntropyLoss
+    cfg = O.model_config("tiny", 2)
+    cfg.pop("depth_head")
+    model = D.DenseCLIP(**copy.deepcopy(cfg), precision="fp32")
+    sd = O.seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 5)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    for n, p in model.named_parameters():
+        p.requires_grad = not (n.startswith('backbone.') or n.startswith('text_encoder.'))
+    img = O.synthetic_images(2, 32, 64, seed=105)
+    seg_t, _, _ = O.synthetic_targets(2, 32, 64, seed=205)
+    out = model(img.cuda(), gt_semantic_seg=seg_t.cuda(), return_loss=True)
+    assert out["depth_output"] is None
+    CrossEntropyLoss(ignore_index=255)(out["main_output"], seg_t.cuda()).backward()
+    sdg = {k: (v.clone().requires_grad_(True) if k.startswith(O.TRAINABLE_PREFIXES) and v.is_floating_point() and 'running_' not in k else v)
+           for k, v in sd.items()}
+    main, depth, _ = O.train_forward(sdg, cfg, img, (32, 64))
+    assert depth is None
+    F.cross_entropy(main, seg_t, ignore_index=255).backward()
+    assert rel_err(out["main_output"], main) < 1e-3
+    named = dict(model.named_parameters())
+    for k, v in sdg.items():
+        if isinstance(v, torch.Tensor) and v.requires_grad:
+            assert named[k].grad is not None and rel_err(named[k].grad, v.grad) < 5e-3, (k, rel_err(named[k].grad, v.grad))
