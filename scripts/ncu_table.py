@@ -24,7 +24,7 @@ agg = collections.OrderedDict()
 for r in data:
     name = re.sub(r'\(.*', '', r[col['Kernel Name']]).replace('void ', '').replace('dclip::', '')
     t = f(r, 'gpu__time_duration.sum')
-    t = t / 1000 if units.get('gpu__time_duration.sum', 'ns').startswith('n') else t   # -> us
+    t = t * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}.get(units.get('gpu__time_duration.sum', 'ns'), 1e-3)   # -> us
     a = agg.setdefault(name, dict(n=0, t=0.0, tensor=[], dr=0.0, dw=0.0, dram=[], occ=[], regs=0, xu=[], issue=[]))
     a['n'] += 1
     a['t'] += t
