@@ -22,6 +22,7 @@ def _dev(t: torch.Tensor) -> int:
 
 
 def _stream(t: torch.Tensor):
+    _dev(t)   # (CPU tensors fail here with DclipError, before torch is asked for a CUDA stream)
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 

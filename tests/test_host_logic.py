@@ -99,3 +99,21 @@ def test_confusion_matrix_and_stats():
     assert cm.tolist() == [[1, 0, 0], [0, 1, 0], [0, 1, 2]]
     _, miou, acc, rmse = dd.reduce_eval_stats(cm, torch.tensor(8.0), torch.tensor(2.0))
     assert abs(acc - 0.8) < 1e-9 and abs(rmse - 2.0) < 1e-9 and abs(miou - (1 + 0.5 + 2 / 3) / 3) < 1e-9
+
+
+def test_training_tail_fails_loudly_without_a_gpu():
+    """The training-mode tail and the native losses have no CPU path: CPU tensors raise DclipError instead of silently
+    falling back to torch (the product path must fail loudly when the CUDA side is unavailable)."""
+    import pytest
+    import torch
+    from denseclip_vit_multimodal_b200 import _lib, train_tail as T
+    from denseclip_vit_multimodal_b200.losses import CrossEntropyLoss, SILogLoss
+    x = torch.randn(8, 16)
+    with pytest.raises(_lib.DclipError):
+        T.col_stats(x, 1e-5)
+    with pytest.raises(_lib.DclipError):
+        CrossEntropyLoss(ignore_index=255)(torch.randn(1, 3, 4, 4, requires_grad=True), torch.zeros(1, 4, 4, dtype=torch.long))
+    with pytest.raises(_lib.DclipError):
+        SILogLoss()(torch.rand(1, 1, 4, 4, requires_grad=True) + 0.1, torch.rand(1, 1, 4, 4) + 0.1)
+    with pytest.raises(ValueError):
+        SILogLoss(reduction="none")          # same constructor contract as denseclip/losses.py:15-19
