@@ -418,18 +418,21 @@ class DenseCLIP(nn.Module):
         #    The branch (vis/global projection, ContextDecoder, score map: ~50 mostly latency-bound launches) shares nothing
         #    with the neck / heads branch below, so it runs on a side stream and the two overlap (also inside a captured
         #    graph, where the fork/join become graph dependencies).  DCLIP_OVERLAP_TAIL=0 runs them back to back.
-        side = self._tail_stream(img.device) if _OVERLAP_TAIL else None
-        if side is not None:
-            main = torch.cuda.current_stream(img.device)
-            fork = torch.cuda.Event()
-            fork.record(main)
-            side.wait_event(fork)
-            with torch.cuda.stream(side):
-                text, score, _ = self._tail_native(tokens, gh, gw)
-                join = torch.cuda.Event()
-                join.record(side)
-        else:
+        #    The branch ALWAYS runs on the model's own side stream (the few-query attention keeps its key-split scratch per
+        #    stream and may not grow it during graph capture: warm-up and capture must see the same stream); with
+        #    DCLIP_OVERLAP_TAIL=0 the main stream simply joins before the neck instead of after the heads.
+        side = self._tail_stream(img.device)
+        main = torch.cuda.current_stream(img.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
             text, score, _ = self._tail_native(tokens, gh, gw)
+            join = torch.cuda.Event()
+            join.record(side)
+        if not _OVERLAP_TAIL:
+            main.wait_event(join)
+            side = None
         self.last_text_embeddings, self.last_score_map = text, score
         if self.training:
             # training mode (train_denseclip.py:1226): BatchNorm on batch statistics, Dropout, and a tape through neck / heads /
